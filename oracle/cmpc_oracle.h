@@ -110,6 +110,11 @@ int cmpc_oracle_ipm_solve_fn(const cmpc_oracle_nlp_fn* nlp, int N, const cmpc_or
                              const double* p, const double* lbg, const double* ubg, double* x, double* lam_g,
                              cmpc_oracle_ipm_stats* stats);
 
+/* Same solver on a CasADi-generated shared object exporting nlp_fg / nlp_jac_fg / nlp_hess_l (oracle/_ref, N = 12). */
+int cmpc_oracle_ipm_solve_casadi(const char* so_path, const cmpc_oracle_ipm_opts* opts, const double* p,
+                                 const double* lbg, const double* ubg, double* x, double* lam_g,
+                                 cmpc_oracle_ipm_stats* stats);
+
 /* batch driver with a pthread pool (cpu_baseline leg of bench.py): instance i uses p+i*np etc. */
 int cmpc_oracle_ipm_solve_batch(const cmpc_oracle_cfg* cfg, const cmpc_oracle_ipm_opts* opts, int batch,
                                 int threads, const double* p, const double* lbg, const double* ubg, double* x,
