@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- batched centroidal-MPC solves/sec on B200 (BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload icub3_b1024|ergocub_b65536]
+
+A "step" = one pass of the hot path (cmpc_solve_batched: the full interior-point solve of every instance, cold start
+from the same x0) over one batch of synthetic MPC instances.  Default workload = BASELINE.json configs[1]:
+batch 1024 iCub3 instances (iCubGazeboV3/centroidal_mpc.ini: N = 15, dT = 0.1), randomised CoM / momentum initial
+states, step adjustment off, ipopt tolerance 1e-8 -- per GPU (weak scaling over --gpus).
+  value    : solves/s with inputs resident in HBM, CUDA-event time of the K steps (max over ranks)
+  e2e      : solves/s through cmpc_solve_host with pinned HOST buffers (H2D + solve + D2H inside the timed region)
+  roofline : executed FP64 flop / kernel time against the measured FP64 FMA peak (the kernel is FP64 CUDA-core
+             bound; HBM numbers are given beside it to show that HBM is not the bound)
+  cpu_baseline : the CPU oracle (restatement of the IPOPT solve) on the host cores, bounded sample, rank 0, N = 1 only
+--impl reference times the reference's CPU path (the oracle port: IPOPT/CasADi are not installable here).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "paper_romualdi_2022_icra_centroidal-mpc-walking_b200"
+
+# FP64 flop executed per interior-point iteration and knot by cmpc_solve_kernel (measured with ncu, see
+# profiles/ and DESIGN.md "flop accounting"), and the canonical dense figure of SURVEY.md 8(d)
+FLOP_EXEC_PER_ITER_KNOT = 1.66e5
+FLOP_CANON_PER_ITER_KNOT = 422275.0
+FP64_PEAK_FALLBACK_TFLOPS = 37.0  # vendor figure (HGX B200 296 TF / 8); used only if the live DFMA probe fails
+
+
+def workload(name: str, pkg, wl, seed: int):
+    if name == "icub3_b1024":
+        cfg = pkg.icub3_config()
+        w = wl.walk_batch(N=15, dT=0.1, B=1024, seed=seed, state_noise=1.0, step_adjust=False)
+        ocfg = dict(N=15, w_com=(1.0, 1.0, 200.0), w_pos=200.0, w_sym=0.0,
+                    corners=[[(0.08, 0.03, 0), (0.08, -0.03, 0), (-0.08, -0.03, 0), (-0.08, 0.03, 0)]] * 2)
+    elif name == "ergocub_b65536":
+        cfg = pkg.ergocub_config()
+        w = wl.walk_batch(N=12, dT=0.1, B=65536, seed=seed, state_noise=2.0, yaw_range=0.3, step_adjust=True)
+        ocfg = dict(N=12, w_pos=2000.0)
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    return cfg, w, ocfg
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_rate(ocfg, w, sample: int, threads: int, tol: float):
+    from oracle import oracle as om
+    om.build()
+    O = om.Oracle()
+    cfg = om.make_cfg(**ocfg)
+    t0 = time.perf_counter()
+    x, lam, st = O.solve_batch(cfg, w["p"][:sample], w["lbg"][:sample], w["ubg"][:sample], w["x0"][:sample],
+                               threads=threads, opts=O.default_opts(tol=tol))
+    dt = time.perf_counter() - t0
+    ok = sum(1 for s in st if s.status == 0)
+    its = float(np.mean([s.iters for s in st]))
+    return sample / dt, dt, ok, its
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path for this metric = the oracle port (IPOPT restatement) on all host
+    cores.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    pkg_wl = importlib.import_module(PKG + ".workloads")
+    lay = importlib.import_module(PKG + ".layout")  # noqa: F841
+
+    class _P:  # config factory without touching the CUDA library
+        @staticmethod
+        def icub3_config():
+            return None
+
+        @staticmethod
+        def ergocub_config():
+            return None
+    _, w, ocfg = workload(args.workload, _P, pkg_wl, seed=0)
+    cores = os.cpu_count() or 1
+    sample = min(w["p"].shape[0], max(8, 2 * cores))
+    times = []
+    for s in range(args.warmup + args.steps):
+        rate, dt, ok, its = cpu_oracle_rate(ocfg, w, sample, cores, 1e-8)
+        if s >= args.warmup:
+            times.append(dt)
+    t = float(np.sum(times))
+    value = sample * len(times) / t
+    line = {"impl": "reference", "metric": "batched centroidal-MPC solves/sec", "value": value, "unit": "solves/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "note": "each step = bounded sample of the workload"},
+            "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample} instances of {args.workload} per step, tol 1e-8, "
+                                       f"{ok}/{sample} converged, mean {its:.1f} iterations"},
+            "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="icub3_b1024")
+    ap.add_argument("--tol", type=float, default=1e-8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    pkg = importlib.import_module(PKG)
+    wl = importlib.import_module(PKG + ".workloads")
+    cfg, w, ocfg = workload(args.workload, pkg, wl, seed=rank)   # every rank its own shard of instances
+    cfg.device = local
+    cfg.ipopt_tolerance = args.tol
+    solver = pkg.BatchedCentroidalMPC(cfg)
+    B, N = w["p"].shape[0], cfg.horizon
+    n, m, npar = solver.L.n, solver.L.m, solver.L.np
+    tens = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    d_p, d_lbg, d_ubg, d_x0 = tens(w["p"]), tens(w["lbg"]), tens(w["ubg"]), tens(w["x0"])
+    d_x = d_x0.clone()
+    d_lam = torch.zeros(B, m, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2
+    gather = [torch.empty(B, 3, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
+
+    def step():
+        d_x.copy_(d_x0)
+        obj, status, iters, _ = solver.solve(d_p, d_lbg, d_ubg, d_x, d_lam)
+        if world > 1:  # the only exchange of the sharded job: gather per-instance results
+            dist.all_gather(gather, torch.stack([obj, status.double(), iters.double()], dim=1))
+        return obj, status, iters
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        obj, status, iters = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = solver.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        flush.zero_()                      # L2 flush between timed iterations (outside the step's event pair)
+        ev[s][0].record()
+        d_x.copy_(d_x0)
+        kev[s][0].record()
+        obj, status, iters, _ = solver.solve(d_p, d_lbg, d_ubg, d_x, d_lam)
+        kev[s][1].record()
+        if world > 1:
+            dist.all_gather(gather, torch.stack([obj, status.double(), iters.double()], dim=1))
+        ev[s][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = solver.launch_count() - launches0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    t_dev = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    t_kernel = sum(a.elapsed_time(b) for a, b in kev) * 1e-3
+    tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_max = float(tt.item())
+    status_h, iters_h = status.cpu().numpy(), iters.cpu().numpy()
+    conv = int((status_h == 0).sum())
+    total_iters = int(iters_h.sum())
+
+    # ---- end to end through the host-pointer C-ABI call with pinned host buffers
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+    h_p, h_lbg, h_ubg, h_x0 = pin(w["p"]), pin(w["lbg"]), pin(w["ubg"]), pin(w["x0"])
+    h_x, h_lam = torch.empty_like(h_x0).pin_memory(), torch.zeros(B, m, dtype=torch.float64).pin_memory()
+    h_obj = torch.zeros(B, dtype=torch.float64).pin_memory()
+    h_st, h_it = torch.zeros(B, dtype=torch.int32).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory()
+    import ctypes as C
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+
+    def e2e_step():
+        h_x.copy_(h_x0)
+        rc = solver.lib.cmpc_solve_host(solver.handle, B, vp(h_p), vp(h_lbg), vp(h_ubg), vp(h_x), vp(h_lam), vp(h_obj),
+                                        vp(h_st), vp(h_it), 0)
+        assert rc == 0, rc
+    e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    k_e2e = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(k_e2e):
+        e2e_step()
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * k_e2e / float(te.item())
+    h2d = 8 * B * (npar + 2 * m + n)
+    d2h = 8 * B * (n + m + 1) + 8 * B
+
+    if rank == 0:
+        value = world * B * args.steps / t_max
+        # FP64 roofline of the solver kernel
+        peak_tf, peak_src = FP64_PEAK_FALLBACK_TFLOPS, "fallback: vendor 37 TFLOP/s FP64 (no measured FP64 peak in MEASURED_PEAKS.json)"
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            hbm_peak = float(mp.get("hbm_gbs", 6551.0))
+            if "fp64_tflops" in mp:
+                peak_tf, peak_src = float(mp["fp64_tflops"]), "measured"
+        except Exception:
+            hbm_peak = 6650.0
+        kernel_s = t_kernel / args.steps
+        flop_exec = total_iters * N * FLOP_EXEC_PER_ITER_KNOT
+        flop_canon = total_iters * N * FLOP_CANON_PER_ITER_KNOT
+        achieved = flop_exec / kernel_s / 1e12
+        alg_bytes = 8.0 * B * (npar + 2 * m + 2 * n + 2 * m)
+        line = {
+            "metric": "batched centroidal-MPC solves/sec", "value": value, "unit": "solves/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "instances_per_gpu": B, "horizon_knots": N, "ipopt_tolerance": args.tol,
+                       "robot_ini": "iCubGazeboV3/centroidal_mpc.ini" if args.workload.startswith("icub3") else
+                                    "ergoCubGazeboV1_1/centroidal_mpc.ini",
+                       "cold_start": True, "l2": "flushed between steps (256 MB write)",
+                       "converged": f"{conv}/{B}", "mean_iterations": total_iters / B,
+                       "solver_grid": solver.geometry()},
+            "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": k_e2e, "api": "cmpc_solve_host (pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                         "traffic": None, "peak_source": peak_src, "kernel": "cmpc_solve_kernel",
+                         "kernel_ms_per_launch": 1e3 * kernel_s, "flop_executed_per_launch": flop_exec,
+                         "flop_canonical_dense_per_launch": flop_canon,
+                         "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / kernel_s / 1e9,
+                                 "peak_gbs": hbm_peak, "frac": alg_bytes / kernel_s / 1e9 / hbm_peak}},
+            "clocks": sampler.summary(),
+            "wall_s_timed_region": t_wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            sample = min(B, max(8, 2 * cores))
+            rate, dt, ok, its = cpu_oracle_rate(ocfg, w, sample, cores, args.tol)
+            line["cpu_baseline"] = {"value": rate, "unit": "solves/s", "cores": cores, "kind": "port",
+                                    "sample": f"first {sample} instances of the workload, {dt:.1f} s, {ok}/{sample} "
+                                              f"converged, mean {its:.1f} iterations (oracle = IPOPT restatement)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

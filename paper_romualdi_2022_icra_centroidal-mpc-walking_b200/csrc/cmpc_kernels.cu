@@ -1,0 +1,591 @@
+// cmpc_kernels.cu -- sm_100a kernels and the C ABI (include/cmpc_b200.h) of the batched centroidal-MPC solve.
+//
+// Kernel inventory (see DESIGN.md for the roofline of each):
+//   cmpc_solve_kernel     persistent CTAs, one MPC instance per CTA at a time (atomic work queue): the whole
+//                         interior-point solve incl. the per-knot Riccati factorisation in shared memory
+//   cmpc_shift_kernel     warm-start shift of x / lam_g by one knot (HBM bound, coalesced, staged in shared memory)
+//   cmpc_eval_kernel      f, grad f, g of the NLP (parity surface for nlp_fg / nlp_jac_fg)
+//   cmpc_jac_kernel / cmpc_hess_kernel   entry-wise CSC jacobian / hessian (parity surface)
+//   cmpc_plant_kernel     RK4 centroidal dynamics of the closed-loop plant
+// No CPU fallback exists: every entry point needs a CUDA device and says so when there is none.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/cmpc_b200.h"
+#include "cmpc_sparse.cuh"
+
+namespace cmpc {
+
+// ------------------------------------------------------------------------------------------------ device CTA context
+struct DevCta {
+    int tid, nt, warp, lane, wsize;
+    double* red;  // >= 64 doubles of shared memory
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+    __device__ __forceinline__ void syncwarp() { __syncwarp(); }
+
+    template <int K, class Op>
+    __device__ __forceinline__ void allreduce(double* v, Op op)
+    {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double x = v[k];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) x = op(x, __shfl_xor_sync(0xffffffffu, x, off));
+            v[k] = x;
+        }
+        const int nw = nt >> 5;
+        if (lane == 0)
+            for (int k = 0; k < K; ++k) red[warp * K + k] = v[k];
+        __syncthreads();
+        for (int k = 0; k < K; ++k) {
+            double x = red[k];
+            for (int w2 = 1; w2 < nw; ++w2) x = op(x, red[w2 * K + k]);
+            v[k] = x;
+        }
+        __syncthreads();
+    }
+    template <int K> __device__ __forceinline__ void sumv(double* v) { allreduce<K>(v, [](double a, double b) { return a + b; }); }
+    template <int K> __device__ __forceinline__ void maxv(double* v) { allreduce<K>(v, [](double a, double b) { return fmax(a, b); }); }
+    template <int K> __device__ __forceinline__ void minv(double* v) { allreduce<K>(v, [](double a, double b) { return fmin(a, b); }); }
+    __device__ __forceinline__ double sum(double x) { sumv<1>(&x); return x; }
+    __device__ __forceinline__ double max(double x) { maxv<1>(&x); return x; }
+};
+
+__device__ __forceinline__ DevCta make_cta(double* red)
+{
+    DevCta c;
+    c.tid = threadIdx.x; c.nt = blockDim.x; c.warp = threadIdx.x >> 5; c.lane = threadIdx.x & 31; c.wsize = 32;
+    c.red = red;
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+#ifndef CMPC_MIN_CTAS
+#define CMPC_MIN_CTAS 3
+#endif
+
+__global__ void __launch_bounds__(128, CMPC_MIN_CTAS)
+cmpc_solve_kernel(Config cfg, int batch, const double* __restrict__ p, const double* __restrict__ lbg,
+                  const double* __restrict__ ubg, double* x, double* lam, double* obj, int* status, int* iters,
+                  int warm_duals, double* work, size_t work_stride, unsigned int* counter)
+{
+    extern __shared__ double smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    __shared__ int s_inst;
+    DevCta cta = make_cta(sm.red);
+    const int N = cfg.N, n = dim_x(N), np = dim_p(N), m = dim_g(N);
+    Work w;
+    work_carve(work + (size_t)blockIdx.x * work_stride, N, w);
+    for (;;) {
+        if (threadIdx.x == 0) s_inst = (int)atomicAdd(counter, 1u);
+        __syncthreads();
+        const int inst = s_inst;
+        __syncthreads();
+        if (inst >= batch) break;
+        Instance in{p + (size_t)inst * np, lbg + (size_t)inst * m, ubg + (size_t)inst * m};
+        Result r = ipm_solve(cta, cfg, in, w, sm, x + (size_t)inst * n, lam ? lam + (size_t)inst * m : nullptr, warm_duals);
+        if (threadIdx.x == 0) {
+            if (obj) obj[inst] = r.obj;
+            if (status) status[inst] = r.status;
+            if (iters) iters[inst] = r.iters;
+        }
+    }
+}
+
+// warm-start shift: one CTA per instance, the vector is staged in shared memory so that loads and stores are coalesced
+CMPC_HD int shift_src_x(int N, int i)
+{
+    const int nb = 9 * (N + 1);
+    if (i < nb) { int blk = i / (3 * (N + 1)), r = i % (3 * (N + 1)), k = r / 3; return k < N ? i + 3 : i; (void)blk; }
+    int r = (i - nb) % (18 * N + 3);
+    if (r < 3 * (N + 1)) return r / 3 < N ? i + 3 : i;
+    r -= 3 * (N + 1);
+    return (r % (3 * N)) / 3 < N - 1 ? i + 3 : i;  // vel, forces: N columns
+}
+CMPC_HD int shift_src_g(int N, int r)
+{
+    if (r < NS) return r;  // initial-condition multipliers are recomputed by the next solve
+    int q = r - NS;
+    if (q < 15 * N) return (q % (3 * N)) / 3 < N - 1 ? r + 3 : r;
+    q = (q - 15 * N) % (19 * N);
+    if (q < 3 * N) return q / 3 < N - 1 ? r + 3 : r;
+    q -= 3 * N;
+    return q / 16 < N - 1 ? r + 16 : r;
+}
+__global__ void cmpc_shift_kernel(int N, int batch, double* x, double* lam)
+{
+    extern __shared__ double buf[];
+    const int n = dim_x(N), m = dim_g(N);
+    for (int inst = blockIdx.x; inst < batch; inst += gridDim.x) {
+        double* xi = x + (size_t)inst * n;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) buf[i] = xi[i];
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) xi[i] = buf[shift_src_x(N, i)];
+        __syncthreads();
+        if (lam) {
+            double* li = lam + (size_t)inst * m;
+            for (int i = threadIdx.x; i < m; i += blockDim.x) buf[i] = li[i];
+            __syncthreads();
+            for (int i = threadIdx.x; i < m; i += blockDim.x) li[i] = buf[shift_src_g(N, i)];
+            __syncthreads();
+        }
+    }
+}
+
+// f, grad f, g: one CTA per instance with the solver's own evaluation routines
+__global__ void cmpc_eval_kernel(Config cfg, int batch, const double* __restrict__ x, const double* __restrict__ p,
+                                 double* f, double* grad, double* g, double* gscratch)
+{
+    extern __shared__ double sd[];  // N * SD_STRIDE stage data + 64 reduction scratch
+    const int N = cfg.N, n = dim_x(N), np = dim_p(N), m = dim_g(N);
+    DevCta cta = make_cta(sd + N * SD_STRIDE);
+    for (int inst = blockIdx.x; inst < batch; inst += gridDim.x) {
+        Instance in{p + (size_t)inst * np, nullptr, nullptr};
+        const double* xi = x + (size_t)inst * n;
+        stage_data(cta, cfg, in, xi, sd);
+        double* gi = g ? g + (size_t)inst * m : gscratch + (size_t)blockIdx.x * m;
+        eval_g(cta, cfg, in, xi, sd, gi);
+        double fv = eval_f(cta, cfg, in, xi, grad ? grad + (size_t)inst * n : (double*)nullptr);
+        if (grad) {  // dcom carries no cost and is not written by eval_f
+            for (int it = threadIdx.x; it < 3 * (N + 1); it += blockDim.x) grad[(size_t)inst * n + x_dcom(N, 0) + it] = 0.0;
+        }
+        if (f && threadIdx.x == 0) f[inst] = fv;
+        __syncthreads();
+    }
+}
+
+__global__ void cmpc_jac_kernel(Config cfg, int batch, const double* __restrict__ x, const double* __restrict__ p,
+                                const int* __restrict__ slot, double* jnz)
+{
+    const int N = cfg.N, n = dim_x(N), np = dim_p(N), nnz = nnz_jac(N);
+    const long long total = (long long)batch * nnz;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        int inst = (int)(t / nnz), e = (int)(t % nnz), row, col;
+        double v = jac_entry(cfg, x + (size_t)inst * n, p + (size_t)inst * np, e, row, col);
+        jnz[(size_t)inst * nnz + slot[e]] = v;
+    }
+}
+
+__global__ void cmpc_hess_kernel(Config cfg, int batch, const double* __restrict__ p, double lam_f,
+                                 const double* __restrict__ lam_g, const int* __restrict__ slot, double* hnz)
+{
+    const int N = cfg.N, np = dim_p(N), m = dim_g(N), nnz = nnz_hess(N);
+    const long long total = (long long)batch * nnz;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        int inst = (int)(t / nnz), e = (int)(t % nnz), row, col;
+        double v = hess_entry(cfg, p + (size_t)inst * np, lam_f, lam_g + (size_t)inst * m, e, row, col);
+        hnz[(size_t)inst * nnz + slot[e]] = v;
+    }
+}
+
+// closed-loop plant: RK4 of  d(com) = dcom, d(dcom) = g + ext_f + sum en f, d(h) = ext_t + sum en (R r_j + pos - com) x f
+// (BLF CentroidalDynamics with unit mass, WholeBodyQPBlock.cpp:1039-1041, 1083-1090, 1150-1158); forces held constant
+__global__ void cmpc_plant_kernel(Config cfg, int batch, const double* __restrict__ x, const double* __restrict__ p,
+                                  const double* __restrict__ ext, double* state, double dt, int substeps)
+{
+    const int N = cfg.N, n = dim_x(N), np = dim_p(N);
+    for (int inst = blockIdx.x * blockDim.x + threadIdx.x; inst < batch; inst += gridDim.x * blockDim.x) {
+        const double* xi = x + (size_t)inst * n;
+        const double* pi = p + (size_t)inst * np;
+        double F[3] = {0, 0, GRAV_Z}, T0[3] = {0, 0, 0};  // dh = T0 - com x Fc  with  Fc = sum of contact forces
+        double Fc[3] = {0, 0, 0};
+        if (ext) {
+            for (int a = 0; a < 3; ++a) { F[a] += ext[(size_t)inst * 6 + a]; T0[a] += ext[(size_t)inst * 6 + 3 + a]; }
+        }
+        for (int c = 0; c < NC; ++c) {
+            double en = pi[p_en(N, c, 0)];
+            const double* R = pi + p_rot(N, c, 0);
+            for (int j = 0; j < NJ; ++j) {
+                const double* cr = cfg.corner[c][j];
+                double arm[3], f[3], t[3];
+                for (int a = 0; a < 3; ++a) {
+                    arm[a] = R[a] * cr[0] + R[3 + a] * cr[1] + R[6 + a] * cr[2] + xi[x_pos(N, c, 0) + a];
+                    f[a] = en * xi[x_frc(N, c, j, 0) + a];
+                }
+                cross3(arm, f, t);
+                for (int a = 0; a < 3; ++a) { Fc[a] += f[a]; T0[a] += t[a]; }
+            }
+        }
+        for (int a = 0; a < 3; ++a) F[a] += Fc[a];
+        double* s = state + (size_t)inst * 9;
+        double com[3] = {s[0], s[1], s[2]}, dcom[3] = {s[3], s[4], s[5]}, h[3] = {s[6], s[7], s[8]};
+        for (int it = 0; it < substeps; ++it) {
+            // the vector field is affine in (com, dcom): RK4 written out
+            double k1c[3], k2c[3], k3c[3], k4c[3], k1h[3], k2h[3], k3h[3], k4h[3], tmp[3], cx[3];
+            for (int a = 0; a < 3; ++a) k1c[a] = dcom[a];
+            cross3(com, Fc, cx); for (int a = 0; a < 3; ++a) k1h[a] = T0[a] - cx[a];
+            for (int a = 0; a < 3; ++a) { k2c[a] = dcom[a] + 0.5 * dt * F[a]; tmp[a] = com[a] + 0.5 * dt * k1c[a]; }
+            cross3(tmp, Fc, cx); for (int a = 0; a < 3; ++a) k2h[a] = T0[a] - cx[a];
+            for (int a = 0; a < 3; ++a) { k3c[a] = dcom[a] + 0.5 * dt * F[a]; tmp[a] = com[a] + 0.5 * dt * k2c[a]; }
+            cross3(tmp, Fc, cx); for (int a = 0; a < 3; ++a) k3h[a] = T0[a] - cx[a];
+            for (int a = 0; a < 3; ++a) { k4c[a] = dcom[a] + dt * F[a]; tmp[a] = com[a] + dt * k3c[a]; }
+            cross3(tmp, Fc, cx); for (int a = 0; a < 3; ++a) k4h[a] = T0[a] - cx[a];
+            for (int a = 0; a < 3; ++a) {
+                com[a] += dt / 6.0 * (k1c[a] + 2.0 * k2c[a] + 2.0 * k3c[a] + k4c[a]);
+                h[a] += dt / 6.0 * (k1h[a] + 2.0 * k2h[a] + 2.0 * k3h[a] + k4h[a]);
+                dcom[a] += dt * F[a];
+            }
+        }
+        for (int a = 0; a < 3; ++a) { s[a] = com[a]; s[3 + a] = dcom[a]; s[6 + a] = h[a]; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static void friction_matrix_host(double mu, double A[NF][3])
+{
+    // BLF Math::LinearizedFrictionCone with one slice per quadrant: the unit circle is sampled every pi/2, each closed
+    // segment gives the half plane  -s*slope*fx + s*fy - s*offset*mu*fz <= 0  (s = -1 below the x axis)
+    const double kPi = 3.14159265358979323846;
+    const int nrows = NF;
+    const double seg = kPi / 2.0;
+    for (int i = 0; i < nrows; ++i) {
+        double a0 = seg * i, a1 = seg * (i + 1), a1w = seg * ((i + 1) % nrows);
+        double x0 = cos(a0), y0 = sin(a0), x1 = cos(a1w), y1 = sin(a1w);
+        double slope = (y1 - y0) / (x1 - x0), offset = y0 - slope * x0;
+        double s = (a0 > kPi || a1 > kPi) ? -1.0 : 1.0;
+        A[i][0] = -s * slope; A[i][1] = s; A[i][2] = -s * offset * mu;
+    }
+}
+
+struct Csc {
+    std::vector<int> colind, row, slot;
+};
+static void build_csc(int N, bool hess, Csc& out)
+{
+    Config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.N = N;
+    const int ne = hess ? hess_emissions(N) : NS + JAC_PER_KNOT * N;
+    const int ncol = dim_x(N);
+    struct T { int r, c, e; };
+    std::vector<T> t(ne);
+    for (int e = 0; e < ne; ++e) {
+        int r, c;
+        if (hess) hess_entry(cfg, nullptr, 0.0, nullptr, e, r, c);
+        else jac_entry(cfg, nullptr, nullptr, e, r, c);
+        t[e] = {r, c, e};
+    }
+    std::sort(t.begin(), t.end(), [](const T& a, const T& b) { return a.c != b.c ? a.c < b.c : (a.r != b.r ? a.r < b.r : a.e < b.e); });
+    out.colind.assign(ncol + 1, 0);
+    out.row.resize(ne);
+    out.slot.resize(ne);
+    for (int i = 0; i < ne; ++i) { out.row[i] = t[i].r; out.slot[t[i].e] = i; out.colind[t[i].c + 1]++; }
+    for (int c = 0; c < ncol; ++c) out.colind[c + 1] += out.colind[c];
+}
+
+}  // namespace cmpc
+
+using namespace cmpc;
+
+struct cmpc_handle_s {
+    Config cfg;
+    cmpc_config user;
+    int device = 0, sm_count = 0, threads = 128, ctas_per_sm = 0, grid = 0, smem = 0;
+    size_t work_stride = 0;
+    double* d_work = nullptr;
+    unsigned int* d_counter = nullptr;
+    int *d_jslot = nullptr, *d_hslot = nullptr;
+    double* d_gscratch = nullptr;
+    // staging buffers of cmpc_solve_host
+    int host_cap = 0;
+    double *d_p = nullptr, *d_lbg = nullptr, *d_ubg = nullptr, *d_x = nullptr, *d_lam = nullptr, *d_obj = nullptr;
+    int *d_status = nullptr, *d_iters = nullptr;
+    long long launches = 0;
+    int last_cuda = 0;
+};
+
+#define CK(call)                                           \
+    do {                                                   \
+        cudaError_t e_ = (call);                           \
+        if (e_ != cudaSuccess) { h->last_cuda = (int)e_; return CMPC_E_CUDA; } \
+    } while (0)
+
+extern "C" {
+
+int cmpc_default_config(cmpc_config* c)
+{
+    if (!c) return CMPC_E_INVALID;
+    memset(c, 0, sizeof *c);
+    c->horizon = 12; c->sampling_time = 0.1; c->number_of_slices = 1; c->static_friction_coefficient = 0.33;
+    c->com_weight[0] = 10; c->com_weight[1] = 10; c->com_weight[2] = 200;
+    c->contact_position_weight = 2e3;
+    for (int a = 0; a < 3; ++a) c->force_rate_of_change_weight[a] = 10;
+    c->angular_momentum_weight = 1e2; c->contact_force_symmetry_weight = 10;
+    const double cr[4][3] = {{0.08, 0.01, 0}, {0.08, -0.01, 0}, {-0.08, -0.01, 0}, {-0.08, 0.01, 0}};
+    for (int k = 0; k < 2; ++k) memcpy(c->corners[k], cr, sizeof cr);
+    c->ipopt_tolerance = 1e-8; c->ipopt_max_iteration = 200; c->mu_init = 0.1; c->bound_relax_factor = 1e-8;
+    c->bound_push = 0.01; c->infinity = 1e19; c->device = 0; c->threads_per_instance = 0; c->ctas_per_sm = 0;
+    return CMPC_OK;
+}
+
+int cmpc_dims(int N, int* n, int* np, int* m, int* nj, int* nh)
+{
+    if (N < 1) return CMPC_E_INVALID;
+    if (n) *n = dim_x(N);
+    if (np) *np = dim_p(N);
+    if (m) *m = dim_g(N);
+    if (nj) *nj = nnz_jac(N);
+    if (nh) *nh = nnz_hess(N);
+    return CMPC_OK;
+}
+
+int cmpc_friction_matrix(double mu, int slices, double* A)
+{
+    if (!A || slices != 1) return CMPC_E_INVALID;
+    double M[NF][3];
+    friction_matrix_host(mu, M);
+    memcpy(A, M, sizeof M);
+    return CMPC_OK;
+}
+
+int cmpc_jac_sparsity(int N, int* colind, int* row)
+{
+    if (N < 1 || !colind || !row) return CMPC_E_INVALID;
+    Csc c; build_csc(N, false, c);
+    memcpy(colind, c.colind.data(), sizeof(int) * c.colind.size());
+    memcpy(row, c.row.data(), sizeof(int) * c.row.size());
+    return CMPC_OK;
+}
+int cmpc_hess_sparsity(int N, int* colind, int* row)
+{
+    if (N < 1 || !colind || !row) return CMPC_E_INVALID;
+    Csc c; build_csc(N, true, c);
+    memcpy(colind, c.colind.data(), sizeof(int) * c.colind.size());
+    memcpy(row, c.row.data(), sizeof(int) * c.row.size());
+    return CMPC_OK;
+}
+
+int cmpc_create(const cmpc_config* u, cmpc_handle* out)
+{
+    if (!u || !out) return CMPC_E_INVALID;
+    *out = nullptr;
+    if (u->horizon < 2 || u->horizon > 256 || !(u->sampling_time > 0) || u->number_of_slices != 1) return CMPC_E_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return CMPC_E_NO_DEVICE;
+    if (u->device < 0 || u->device >= ndev) return CMPC_E_INVALID;
+    cmpc_handle h = new (std::nothrow) cmpc_handle_s;
+    if (!h) return CMPC_E_ALLOC;
+    h->user = *u;
+    Config& c = h->cfg;
+    memset(&c, 0, sizeof c);
+    c.N = u->horizon; c.dT = u->sampling_time;
+    for (int a = 0; a < 3; ++a) { c.w_com[a] = u->com_weight[a]; c.w_rate[a] = u->force_rate_of_change_weight[a]; }
+    c.w_h = u->angular_momentum_weight; c.w_pos = u->contact_position_weight; c.w_sym = u->contact_force_symmetry_weight;
+    memcpy(c.corner, u->corners, sizeof c.corner);
+    friction_matrix_host(u->static_friction_coefficient, c.fricA);
+    c.tol = u->ipopt_tolerance > 0 ? u->ipopt_tolerance : 1e-8;
+    c.max_iter = u->ipopt_max_iteration > 0 ? u->ipopt_max_iteration : 200;
+    c.mu_init = u->mu_init > 0 ? u->mu_init : 0.1;
+    c.bound_relax = u->bound_relax_factor >= 0 ? u->bound_relax_factor : 1e-8;
+    c.bound_push = u->bound_push > 0 ? u->bound_push : 0.01;
+    c.inf_bound = u->infinity > 0 ? u->infinity : 1e19;
+    h->device = u->device;
+    cudaError_t e = cudaSetDevice(h->device);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, h->device);
+    if (e != cudaSuccess) { delete h; return CMPC_E_CUDA; }
+    h->sm_count = prop.multiProcessorCount;
+    h->threads = 128;  // the kernel is compiled with __launch_bounds__(128, .)
+    h->smem = (int)sizeof(Smem);
+    e = cudaFuncSetAttribute(cmpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
+    int occ = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cmpc_solve_kernel, h->threads, h->smem);
+    if (e != cudaSuccess || occ < 1) { h->last_cuda = (int)e; delete h; return CMPC_E_CUDA; }
+    h->ctas_per_sm = (u->ctas_per_sm > 0 && u->ctas_per_sm < occ) ? u->ctas_per_sm : occ;
+    h->grid = h->sm_count * h->ctas_per_sm;  // persistent grid: a multiple of the SM count
+    h->work_stride = ((size_t)work_doubles(c.N) + 15) & ~(size_t)15;
+    Csc jc, hc;
+    build_csc(c.N, false, jc);
+    build_csc(c.N, true, hc);
+    if (cudaMalloc(&h->d_work, sizeof(double) * h->work_stride * h->grid) != cudaSuccess ||
+        cudaMalloc(&h->d_counter, sizeof(unsigned int)) != cudaSuccess ||
+        cudaMalloc(&h->d_jslot, sizeof(int) * jc.slot.size()) != cudaSuccess ||
+        cudaMalloc(&h->d_hslot, sizeof(int) * hc.slot.size()) != cudaSuccess ||
+        cudaMalloc(&h->d_gscratch, sizeof(double) * dim_g(c.N) * h->sm_count * 4) != cudaSuccess) {
+        cmpc_destroy(h);
+        return CMPC_E_ALLOC;
+    }
+    cudaMemset(h->d_work, 0, sizeof(double) * h->work_stride * h->grid);
+    cudaMemcpy(h->d_jslot, jc.slot.data(), sizeof(int) * jc.slot.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(h->d_hslot, hc.slot.data(), sizeof(int) * hc.slot.size(), cudaMemcpyHostToDevice);
+    *out = h;
+    return CMPC_OK;
+}
+
+int cmpc_destroy(cmpc_handle h)
+{
+    if (!h) return CMPC_E_INVALID;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_work); cudaFree(h->d_counter); cudaFree(h->d_jslot); cudaFree(h->d_hslot); cudaFree(h->d_gscratch);
+    cudaFree(h->d_p); cudaFree(h->d_lbg); cudaFree(h->d_ubg); cudaFree(h->d_x); cudaFree(h->d_lam); cudaFree(h->d_obj);
+    cudaFree(h->d_status); cudaFree(h->d_iters);
+    delete h;
+    return CMPC_OK;
+}
+
+int cmpc_solve_batched(cmpc_handle h, int batch, const double* d_p, const double* d_lbg, const double* d_ubg,
+                       double* d_x, double* d_lam_g, double* d_obj, int* d_status, int* d_iters, int warm_duals,
+                       void* stream)
+{
+    if (!h || batch < 0 || !d_p || !d_lbg || !d_ubg || !d_x) return CMPC_E_INVALID;
+    if (batch == 0) return CMPC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
+    int grid = std::min(batch, h->grid);
+    cmpc_solve_kernel<<<grid, h->threads, h->smem, st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj, d_status,
+                                                         d_iters, warm_duals, h->d_work, h->work_stride, h->d_counter);
+    h->launches++;
+    CK(cudaGetLastError());
+    return CMPC_OK;
+}
+
+static int ensure_host_staging(cmpc_handle h, int batch)
+{
+    if (batch <= h->host_cap) return CMPC_OK;
+    const int N = h->cfg.N;
+    cudaFree(h->d_p); cudaFree(h->d_lbg); cudaFree(h->d_ubg); cudaFree(h->d_x); cudaFree(h->d_lam); cudaFree(h->d_obj);
+    cudaFree(h->d_status); cudaFree(h->d_iters);
+    h->host_cap = 0;
+    size_t b = (size_t)batch;
+    if (cudaMalloc(&h->d_p, 8 * b * dim_p(N)) != cudaSuccess || cudaMalloc(&h->d_lbg, 8 * b * dim_g(N)) != cudaSuccess ||
+        cudaMalloc(&h->d_ubg, 8 * b * dim_g(N)) != cudaSuccess || cudaMalloc(&h->d_x, 8 * b * dim_x(N)) != cudaSuccess ||
+        cudaMalloc(&h->d_lam, 8 * b * dim_g(N)) != cudaSuccess || cudaMalloc(&h->d_obj, 8 * b) != cudaSuccess ||
+        cudaMalloc(&h->d_status, 4 * b) != cudaSuccess || cudaMalloc(&h->d_iters, 4 * b) != cudaSuccess)
+        return CMPC_E_ALLOC;
+    h->host_cap = batch;
+    return CMPC_OK;
+}
+
+int cmpc_solve_host(cmpc_handle h, int batch, const double* p, const double* lbg, const double* ubg, double* x,
+                    double* lam_g, double* obj, int* status, int* iters, int warm_duals)
+{
+    if (!h || batch < 0 || !p || !lbg || !ubg || !x) return CMPC_E_INVALID;
+    if (batch == 0) return CMPC_OK;
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_host_staging(h, batch);
+    if (rc) return rc;
+    const int N = h->cfg.N;
+    size_t b = (size_t)batch;
+    CK(cudaMemcpyAsync(h->d_p, p, 8 * b * dim_p(N), cudaMemcpyHostToDevice, 0));
+    CK(cudaMemcpyAsync(h->d_lbg, lbg, 8 * b * dim_g(N), cudaMemcpyHostToDevice, 0));
+    CK(cudaMemcpyAsync(h->d_ubg, ubg, 8 * b * dim_g(N), cudaMemcpyHostToDevice, 0));
+    CK(cudaMemcpyAsync(h->d_x, x, 8 * b * dim_x(N), cudaMemcpyHostToDevice, 0));
+    if (warm_duals && lam_g) CK(cudaMemcpyAsync(h->d_lam, lam_g, 8 * b * dim_g(N), cudaMemcpyHostToDevice, 0));
+    rc = cmpc_solve_batched(h, batch, h->d_p, h->d_lbg, h->d_ubg, h->d_x, h->d_lam, h->d_obj, h->d_status, h->d_iters,
+                            warm_duals && lam_g, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(x, h->d_x, 8 * b * dim_x(N), cudaMemcpyDeviceToHost, 0));
+    if (lam_g) CK(cudaMemcpyAsync(lam_g, h->d_lam, 8 * b * dim_g(N), cudaMemcpyDeviceToHost, 0));
+    if (obj) CK(cudaMemcpyAsync(obj, h->d_obj, 8 * b, cudaMemcpyDeviceToHost, 0));
+    if (status) CK(cudaMemcpyAsync(status, h->d_status, 4 * b, cudaMemcpyDeviceToHost, 0));
+    if (iters) CK(cudaMemcpyAsync(iters, h->d_iters, 4 * b, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    return CMPC_OK;
+}
+
+int cmpc_shift_warmstart(cmpc_handle h, int batch, double* d_x, double* d_lam_g, void* stream)
+{
+    if (!h || batch < 0 || !d_x) return CMPC_E_INVALID;
+    if (batch == 0) return CMPC_OK;
+    CK(cudaSetDevice(h->device));
+    const int N = h->cfg.N;
+    int grid = std::min(batch, h->sm_count * 8);
+    size_t smem = sizeof(double) * dim_g(N);
+    cmpc_shift_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(N, batch, d_x, d_lam_g);
+    h->launches++;
+    CK(cudaGetLastError());
+    return CMPC_OK;
+}
+
+int cmpc_eval_fg(cmpc_handle h, int batch, const double* d_x, const double* d_p, double* d_f, double* d_g, void* stream)
+{
+    return cmpc_eval_jac_fg(h, batch, d_x, d_p, d_f, nullptr, d_g, nullptr, stream);
+}
+
+int cmpc_eval_jac_fg(cmpc_handle h, int batch, const double* d_x, const double* d_p, double* d_f, double* d_grad,
+                     double* d_g, double* d_jac, void* stream)
+{
+    if (!h || batch < 0 || !d_x || !d_p) return CMPC_E_INVALID;
+    if (batch == 0) return CMPC_OK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = h->cfg.N;
+    if (d_f || d_grad || d_g) {
+        int grid = std::min(batch, h->sm_count * 4);
+        size_t smem = sizeof(double) * (N * SD_STRIDE + 64);
+        cmpc_eval_kernel<<<grid, 128, smem, st>>>(h->cfg, batch, d_x, d_p, d_f, d_grad, d_g, h->d_gscratch);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    if (d_jac) {
+        long long total = (long long)batch * nnz_jac(N);
+        int grid = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16);
+        cmpc_jac_kernel<<<grid, 256, 0, st>>>(h->cfg, batch, d_x, d_p, h->d_jslot, d_jac);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    return CMPC_OK;
+}
+
+int cmpc_eval_hess_l(cmpc_handle h, int batch, const double* d_x, const double* d_p, double lam_f, const double* d_lam_g,
+                     double* d_hess, void* stream)
+{
+    (void)d_x;  // the hessian of the lagrangian does not depend on x
+    if (!h || batch < 0 || !d_p || !d_lam_g || !d_hess) return CMPC_E_INVALID;
+    if (batch == 0) return CMPC_OK;
+    CK(cudaSetDevice(h->device));
+    const int N = h->cfg.N;
+    long long total = (long long)batch * nnz_hess(N);
+    int grid = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16);
+    cmpc_hess_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->cfg, batch, d_p, lam_f, d_lam_g, h->d_hslot, d_hess);
+    h->launches++;
+    CK(cudaGetLastError());
+    return CMPC_OK;
+}
+
+int cmpc_rollout_plant(cmpc_handle h, int batch, const double* d_x, const double* d_p, const double* d_ext,
+                       double* d_state, double dt, int substeps, void* stream)
+{
+    if (!h || batch < 0 || !d_x || !d_p || !d_state || substeps < 0) return CMPC_E_INVALID;
+    if (batch == 0) return CMPC_OK;
+    CK(cudaSetDevice(h->device));
+    int grid = std::min((batch + 127) / 128, h->sm_count * 8);
+    cmpc_plant_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(h->cfg, batch, d_x, d_p, d_ext, d_state, dt, substeps);
+    h->launches++;
+    CK(cudaGetLastError());
+    return CMPC_OK;
+}
+
+long long cmpc_launch_count(cmpc_handle h) { return h ? h->launches : 0; }
+int cmpc_last_cuda_error(cmpc_handle h) { return h ? h->last_cuda : 0; }
+
+const char* cmpc_error_string(int code)
+{
+    switch (code) {
+        case CMPC_OK: return "ok";
+        case CMPC_E_INVALID: return "invalid argument";
+        case CMPC_E_CUDA: return "CUDA runtime error";
+        case CMPC_E_NO_DEVICE: return "no CUDA device (libcmpc_b200 has no CPU path)";
+        case CMPC_E_ALLOC: return "allocation failed";
+        default: return "unknown error";
+    }
+}
+
+int cmpc_solver_geometry(cmpc_handle h, int* grid, int* threads, int* smem, int* ctas_per_sm, int* sm_count)
+{
+    if (!h) return CMPC_E_INVALID;
+    if (grid) *grid = h->grid;
+    if (threads) *threads = h->threads;
+    if (smem) *smem = h->smem;
+    if (ctas_per_sm) *ctas_per_sm = h->ctas_per_sm;
+    if (sm_count) *sm_count = h->sm_count;
+    return CMPC_OK;
+}
+
+}  // extern "C"

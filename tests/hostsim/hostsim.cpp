@@ -1,0 +1,57 @@
+// tests/hostsim/hostsim.cpp -- TEST-ONLY single-thread build of the CUDA solver source (csrc/cmpc_core.cuh).
+//
+// There is no GPU in the development container, so the solver's math is debugged by compiling the very same
+// __host__ __device__ source with a one-thread "CTA".  This library is built and loaded ONLY by
+// tests/test_hostsim.py (marker: not gpu); the product library never contains or falls back to it.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../paper_romualdi_2022_icra_centroidal-mpc-walking_b200/csrc/cmpc_core.cuh"
+
+namespace {
+struct HostCta {
+    int tid = 0, nt = 1, warp = 0, lane = 0, wsize = 1;
+    void sync() {}
+    void syncwarp() {}
+    double sum(double v) { return v; }
+    double max(double v) { return v; }
+    template <int K> void sumv(double*) {}
+    template <int K> void maxv(double*) {}
+    template <int K> void minv(double*) {}
+};
+}  // namespace
+
+extern "C" int hostsim_solve(const cmpc::Config* cfg, const double* p, const double* lbg, const double* ubg, double* x,
+                             double* lam, int warm_duals, int* iters, double* obj, double* kkt)
+{
+    HostCta cta;
+    std::vector<double> buf(cmpc::work_doubles(cfg->N), 0.0);
+    cmpc::Work w;
+    cmpc::work_carve(buf.data(), cfg->N, w);
+    static cmpc::Smem sm;
+    cmpc::Instance in{p, lbg, ubg};
+    cmpc::Result r = cmpc::ipm_solve(cta, *cfg, in, w, sm, x, lam, warm_duals);
+    *iters = r.iters; *obj = r.obj; *kkt = r.kkt;
+    return r.status;
+}
+
+// debug: run `max_iter` iterations and export the internal state and the last search direction
+extern "C" int hostsim_dump(const cmpc::Config* cfg, const double* p, const double* lbg, const double* ubg, double* x,
+                            double* lam, double* s, double* zL, double* zU, double* sL, double* sU, double* dx, double* dy)
+{
+    HostCta cta;
+    std::vector<double> buf(cmpc::work_doubles(cfg->N), 0.0);
+    cmpc::Work w;
+    cmpc::work_carve(buf.data(), cfg->N, w);
+    static cmpc::Smem sm;
+    cmpc::Instance in{p, lbg, ubg};
+    cmpc::Result r = cmpc::ipm_solve(cta, *cfg, in, w, sm, x, lam, 0);
+    const int q = 38 * cfg->N;
+    std::memcpy(s, w.s, 8 * q); std::memcpy(zL, w.zL, 8 * q); std::memcpy(zU, w.zU, 8 * q);
+    std::memcpy(sL, w.sL, 8 * q); std::memcpy(sU, w.sU, 8 * q);
+    std::memcpy(dx, w.dx, 8 * cmpc::dim_x(cfg->N)); std::memcpy(dy, w.dy, 8 * cmpc::dim_g(cfg->N));
+    return r.status;
+}
+
+extern "C" int hostsim_config_size() { return (int)sizeof(cmpc::Config); }

@@ -1,0 +1,242 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path through the C ABI against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): objective within 1e-6 relative; forces / CoM trajectory / footsteps within 1e-5
+scaled inf-norm (max |delta| / max(1, max |ref|) per group); NLP functions (f, g, grad, jac, hess) within 1e-12 relative
+of the oracle / golden vectors (same arithmetic in a different summation order).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import pkg
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from oracle.oracle import make_cfg  # noqa: E402
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "nlp_kat.npz"))
+ICUB_ORACLE = dict(N=15, w_com=(1.0, 1.0, 200.0), w_pos=200.0, w_sym=0.0,
+                   corners=[[(0.08, 0.03, 0), (0.08, -0.03, 0), (-0.08, -0.03, 0), (-0.08, 0.03, 0)]] * 2)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+
+
+def rel(a, b):
+    return np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(1.0, np.max(np.abs(b)))
+
+
+def groups(L):
+    N = L.N
+    g = {"com": np.arange(0, 3 * (N + 1)), "dcom": np.arange(L.x_dcom(0), L.x_dcom(0) + 3 * (N + 1)),
+         "h": np.arange(L.x_h(0), L.x_h(0) + 3 * (N + 1))}
+    pos, frc = [], []
+    for c in range(2):
+        pos += list(range(L.x_pos(c, 0), L.x_pos(c, 0) + 3 * (N + 1)))
+        frc += list(range(L.x_frc(c, 0, 0), L.x_frc(c, 0, 0) + 12 * N))
+    g["footsteps"] = np.array(pos)
+    g["forces"] = np.array(frc)
+    return g
+
+
+def compare_solutions(L, x, xo, obj, obj_o):
+    assert abs(obj - obj_o) <= 1e-6 * max(1.0, abs(obj_o)), (obj, obj_o)
+    for name, idx in groups(L).items():
+        err = np.max(np.abs(x[idx] - xo[idx])) / max(1.0, np.max(np.abs(xo[idx])))
+        assert err <= 1e-5, (name, err)
+
+
+@pytest.fixture(scope="module")
+def solver12():
+    P = pkg()
+    s = P.BatchedCentroidalMPC(P.ergocub_config(contact_position_weight=200.0))  # weights of the reference's tmp.c
+    yield s
+    s.close()
+
+
+@pytest.mark.parametrize("variant,kw", [("tmp", {}), ("jit", dict(com_weight=(10.0, 100.0, 200.0), contact_force_symmetry_weight=100.0))])
+def test_nlp_functions_match_golden_vectors(variant, kw):
+    """f, g, grad f, jac (CSC), hess (CSC) of the CUDA kernels vs the vectors generated from the reference's tmp.c"""
+    P = pkg()
+    s = P.BatchedCentroidalMPC(P.ergocub_config(contact_position_weight=200.0, **kw))
+    nc = int(GOLD["ncases"])
+    x = dev(np.stack([GOLD[f"{variant}_{i}_x"] for i in range(nc)]))
+    p = dev(np.stack([GOLD[f"{variant}_{i}_p"] for i in range(nc)]))
+    f, grad, g, jnz = s.eval_jac_fg(x, p)
+    torch.cuda.synchronize()
+    for i in range(nc):
+        assert abs(f[i].item() - GOLD[f"{variant}_{i}_f"]) <= 1e-12 * abs(GOLD[f"{variant}_{i}_f"])
+        assert rel(g[i].cpu().numpy(), GOLD[f"{variant}_{i}_g"]) < 1e-12
+        assert rel(grad[i].cpu().numpy(), GOLD[f"{variant}_{i}_grad"]) < 1e-12
+        assert rel(jnz[i].cpu().numpy(), GOLD[f"{variant}_{i}_jnz"]) < 1e-12
+        lam = dev(GOLD[f"{variant}_{i}_lam"][None])
+        h = s.eval_hess_l(x[i:i + 1], p[i:i + 1], float(GOLD[f"{variant}_{i}_lamf"]), lam)
+        assert rel(h[0].cpu().numpy(), GOLD[f"{variant}_{i}_hnz"]) < 1e-12
+    s.close()
+
+
+@pytest.mark.parametrize("N", [5, 15, 30])
+def test_nlp_functions_match_oracle_other_horizons(oracle, N):
+    P = pkg()
+    s = P.BatchedCentroidalMPC(P.ergocub_config(horizon=N, contact_position_weight=200.0))
+    cfg = make_cfg(N=N)
+    d = oracle.dims(N)
+    rng = np.random.default_rng(N)
+    B = 4
+    x, p, lam = rng.normal(size=(B, d["n"])), rng.normal(size=(B, d["np"])), 10 * rng.normal(size=(B, d["m"]))
+    f, grad, g, jnz = s.eval_jac_fg(dev(x), dev(p))
+    h = s.eval_hess_l(dev(x), dev(p), 0.9, dev(lam))
+    torch.cuda.synchronize()
+    for b in range(B):
+        fo, grado, go, jo = oracle.jac_fg(cfg, x[b], p[b])
+        ho = oracle.hess_l(cfg, x[b], p[b], 0.9, lam[b])
+        assert abs(f[b].item() - fo) <= 1e-12 * abs(fo)
+        assert rel(g[b].cpu().numpy(), go) < 1e-12 and rel(grad[b].cpu().numpy(), grado) < 1e-12
+        assert rel(jnz[b].cpu().numpy(), jo) < 1e-12 and rel(h[b].cpu().numpy(), ho) < 1e-12
+    s.close()
+
+
+def test_solve_scenario_s0_known_answers(solver12, workloads):
+    """SURVEY.md 8(d) scenario S0 (three pushes): optimum values of the survey's independent prototype"""
+    kat = {(0.0, 0.0, 0.0): 3.208349928306e+01, (0.0, -0.3, 0.0): 1.5201340882e+02, (0.4, 0.0, 0.0): 1.4626640626e+02}
+    for dcom0, fstar in kat.items():
+        s = workloads.scenario_s0(dcom0)
+        x, lam, obj, status, iters = solver12.solve_host(s["p"][None], s["lbg"][None], s["ubg"][None], s["x0"][None])
+        assert status[0] == 0
+        assert abs(obj[0] - fstar) <= 1e-6 * fstar, (obj[0], fstar)
+    L = solver12.L
+    assert abs(x[0][L.x_pos(1, 12)] - 0.11) < 1e-6      # pushed forward: landing at the edge of the step box
+
+
+def test_solve_batch_matches_oracle_ergocub(solver12, oracle, workloads):
+    w = workloads.walk_batch(N=12, B=96, seed=11, state_noise=2.0, yaw_range=0.3)
+    x, lam, obj, status, iters = solver12.solve_host(w["p"], w["lbg"], w["ubg"], w["x0"])
+    xo, lo, st = oracle.solve_batch(make_cfg(), w["p"], w["lbg"], w["ubg"], w["x0"], threads=os.cpu_count() or 4)
+    assert (status == 0).all(), np.bincount(status)
+    same = 0
+    for b in range(96):
+        assert st[b].status == 0
+        compare_solutions(solver12.L, x[b], xo[b], obj[b], st[b].obj)
+        same += 1
+    it_o = np.array([s.iters for s in st])
+    assert same == 96 and np.mean(np.abs(iters - it_o) <= 1) > 0.8   # same local optimum, (nearly) the same path
+
+
+def test_solve_batch_matches_oracle_icub3_no_step_adjustment(oracle, workloads):
+    P = pkg()
+    s = P.BatchedCentroidalMPC(P.icub3_config())
+    w = workloads.walk_batch(N=15, B=48, seed=5, state_noise=1.0, step_adjust=False)
+    x, lam, obj, status, iters = s.solve_host(w["p"], w["lbg"], w["ubg"], w["x0"])
+    xo, lo, st = oracle.solve_batch(make_cfg(**ICUB_ORACLE), w["p"], w["lbg"], w["ubg"], w["x0"], threads=os.cpu_count() or 4)
+    assert (status == 0).all(), np.bincount(status)
+    for b in range(48):
+        compare_solutions(s.L, x[b], xo[b], obj[b], st[b].obj)
+    s.close()
+
+
+def test_kkt_conditions_through_oracle_functions(solver12, oracle, workloads):
+    """optimality of the GPU solution measured with the ORACLE's f/g/jac (i.e. independent of the CUDA derivatives)"""
+    w = workloads.walk_batch(N=12, B=16, seed=3, state_noise=1.5, yaw_range=0.2)
+    x, lam, obj, status, iters = solver12.solve_host(w["p"], w["lbg"], w["ubg"], w["x0"])
+    cfg = make_cfg()
+    jc, jr = oracle.jac_sparsity(12)
+    for b in range(16):
+        f, grad, g, jnz = oracle.jac_fg(cfg, x[b], w["p"][b])
+        r = grad.copy()
+        for c in range(555):
+            sl = slice(jc[c], jc[c + 1])
+            r[c] += np.dot(jnz[sl], lam[b][jr[sl]])
+        scale = max(100.0, np.sum(np.abs(lam[b])) / 651) / 100.0
+        assert np.max(np.abs(r)) / scale < 1e-7
+        lb, ub = w["lbg"][b], w["ubg"][b]
+        viol = np.maximum(np.maximum(lb - g, g - ub), 0.0)
+        assert viol.max() < 2e-8 * 2                      # bounds are relaxed by 1e-8 (bound_relax_factor)
+        assert abs(f - obj[b]) <= 1e-10 * abs(f)
+        # sign of the multipliers: >= 0 only at upper bounds, <= 0 only at lower bounds (inequality rows)
+        ineq = ub > lb
+        assert np.all(lam[b][ineq & (g < ub - 1e-5) & (g > lb + 1e-5)] ** 2 < 1e-8)
+
+
+def test_full_size_batch_properties(workloads):
+    """BASELINE config 2 at full size: every instance converges; the result does not depend on the position of an
+    instance in the batch (determinism, bit exact); a converged point is a fixed point of a warm restart."""
+    P = pkg()
+    s = P.BatchedCentroidalMPC(P.icub3_config())
+    w = workloads.walk_batch(N=15, B=1024, seed=0, state_noise=1.0, step_adjust=False)
+    x, lam, obj, status, iters = s.solve_host(w["p"], w["lbg"], w["ubg"], w["x0"])
+    assert (status == 0).all(), np.bincount(status)
+    perm = np.random.default_rng(0).permutation(1024)
+    x2, lam2, obj2, status2, iters2 = s.solve_host(w["p"][perm], w["lbg"][perm], w["ubg"][perm], w["x0"][perm])
+    assert np.array_equal(x2, x[perm]) and np.array_equal(obj2, obj[perm]) and np.array_equal(iters2, iters[perm])
+    x3, lam3, obj3, status3, iters3 = s.solve_host(w["p"][:64], w["lbg"][:64], w["ubg"][:64], x[:64])
+    assert (status3 == 0).all()
+    assert np.max(np.abs(obj3 - obj[:64]) / np.maximum(1.0, np.abs(obj[:64]))) < 1e-7
+    s.close()
+
+
+def test_bad_input_is_reported_not_fatal(solver12, workloads):
+    w = workloads.walk_batch(N=12, B=4, seed=1)
+    w["lbg"][1, 20] = 1.0     # a dynamics row with lbg != ubg
+    w["x0"][2, 5] = np.nan
+    x, lam, obj, status, iters = solver12.solve_host(w["p"], w["lbg"], w["ubg"], w["x0"])
+    assert status[0] == 0 and status[3] == 0 and status[1] == 4 and status[2] == 4
+
+
+def test_warmstart_shift(solver12):
+    L = solver12.L
+    N = 12
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(3, L.n)); lam = rng.normal(size=(3, L.m))
+    dx, dl = dev(x), dev(lam)
+    solver12.shift_warmstart(dx, dl)
+    torch.cuda.synchronize()
+    xs, ls = dx.cpu().numpy(), dl.cpu().numpy()
+    for b in range(3):
+        for blk, cols in ((0, N + 1), (L.x_dcom(0), N + 1), (L.x_h(0), N + 1), (L.x_pos(0, 0), N + 1), (L.x_vel(0, 0), N),
+                          (L.x_frc(0, 2, 0), N), (L.x_pos(1, 0), N + 1), (L.x_frc(1, 3, 0), N)):
+            a = x[b, blk:blk + 3 * cols].reshape(cols, 3)
+            exp = np.vstack([a[1:], a[-1:]])
+            assert np.array_equal(xs[b, blk:blk + 3 * cols].reshape(cols, 3), exp)
+        assert np.array_equal(ls[b, :15], lam[b, :15])
+        a = lam[b, L.g_h(0):L.g_h(0) + 3 * N].reshape(N, 3)
+        assert np.array_equal(ls[b, L.g_h(0):L.g_h(0) + 3 * N].reshape(N, 3), np.vstack([a[1:], a[-1:]]))
+        a = lam[b, L.g_fric(1, 0, 0):L.g_fric(1, 0, 0) + 16 * N].reshape(N, 16)
+        assert np.array_equal(ls[b, L.g_fric(1, 0, 0):L.g_fric(1, 0, 0) + 16 * N].reshape(N, 16), np.vstack([a[1:], a[-1:]]))
+
+
+def test_plant_rk4(solver12, workloads):
+    """closed-loop plant against a numpy RK4 of the same centroidal dynamics"""
+    L = solver12.L
+    w = workloads.walk_batch(N=12, B=5, seed=2, yaw_range=0.3)
+    rng = np.random.default_rng(1)
+    x = w["x0"] + 0.1 * rng.normal(size=w["x0"].shape)
+    state = np.hstack([w["p"][:, L.p_glob():L.p_glob() + 9]]) + 0.01 * rng.normal(size=(5, 9))
+    ext = 0.5 * rng.normal(size=(5, 6))
+    ds = dev(state)
+    solver12.rollout_plant(dev(x), dev(w["p"]), ds, 0.002, 50, ext=dev(ext))
+    torch.cuda.synchronize()
+    out = ds.cpu().numpy()
+    corners = np.array([(0.08, 0.01, 0), (0.08, -0.01, 0), (-0.08, -0.01, 0), (-0.08, 0.01, 0)])
+    for b in range(5):
+        F = np.array([0, 0, -9.80665]) + ext[b, :3]
+        arms, forces = [], []
+        for c in range(2):
+            en = w["p"][b, L.p_en(c, 0)]
+            R = w["p"][b, L.p_rot(c, 0):L.p_rot(c, 0) + 9].reshape(3, 3).T
+            for j in range(4):
+                arms.append(R @ corners[j] + x[b, L.x_pos(c, 0):L.x_pos(c, 0) + 3])
+                forces.append(en * x[b, L.x_frc(c, j, 0):L.x_frc(c, j, 0) + 3])
+        arms, forces = np.array(arms), np.array(forces)
+        F = F + forces.sum(0)
+
+        def fdot(s):
+            com = s[:3]
+            return np.hstack([s[3:6], F, ext[b, 3:] + np.cross(arms - com, forces).sum(0)])
+        s = state[b].copy()
+        for _ in range(50):
+            k1 = fdot(s); k2 = fdot(s + 0.001 * k1); k3 = fdot(s + 0.001 * k2); k4 = fdot(s + 0.002 * k3)
+            s = s + 0.002 / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+        assert np.max(np.abs(out[b] - s)) < 1e-12
