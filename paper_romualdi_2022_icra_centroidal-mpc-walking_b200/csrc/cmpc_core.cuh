@@ -975,8 +975,19 @@ CMPC_FN void costate_backward(Cta& cta, const Config& cfg, const Instance& in, c
 
 // ------------------------------------------------------------------------------------------------ the solver
 // x_io: in = initial guess, out = solution (CasADi order).  lam_io: multipliers of g (out; in when warm_duals).
-template <class Cta>
-CMPC_HD Result ipm_solve(Cta& cta, const Config& cfg, const Instance& in, const Work& w, Smem& sm, double* x_io,
+// linear-algebra policy of the generic (multi-warp CTA) sweeps above; cmpc_warp.cuh has the warp-per-instance one
+struct LinCta {
+    Smem& sm;
+    template <class Cta> CMPC_HD int backward(Cta& cta, const Config& cfg, const Instance& in, const Work& w, double dw)
+    { return riccati_backward(cta, cfg, in, w, sm, dw); }
+    template <class Cta> CMPC_HD void forward(Cta& cta, const Config& cfg, const Instance& in, const Work& w, bool refine)
+    { riccati_forward(cta, cfg, in, w, sm, refine); }
+    template <class Cta> CMPC_HD void refine_back(Cta& cta, const Config& cfg, const Work& w)
+    { refine_backward(cta, cfg, w, sm); }
+};
+
+template <class Cta, class Lin>
+CMPC_HD Result ipm_solve(Cta& cta, const Config& cfg, const Instance& in, const Work& w, Lin& lin, double* x_io,
                          double* lam_io, int warm_duals)
 {
     const int N = cfg.N, n = dim_x(N), m = dim_g(N), npr = N * INEQ_PER_KNOT;
@@ -1087,7 +1098,7 @@ CMPC_HD Result ipm_solve(Cta& cta, const Config& cfg, const Instance& in, const 
                 w.sig[pr] = sg; w.tt[pr] = t;
             }
             cta.sync();
-            rc = riccati_backward(cta, cfg, in, w, sm, dw);
+            rc = lin.backward(cta, cfg, in, w, dw);
             if (rc == 0) break;
             if (dw == 0.0) dw = dw_last == 0.0 ? DW_FIRST : fmax(DW_MIN, KW_MINUS * dw_last);
             else dw *= (dw_last == 0.0 ? KW_PLUS_FIRST : KW_PLUS);
@@ -1095,7 +1106,7 @@ CMPC_HD Result ipm_solve(Cta& cta, const Config& cfg, const Instance& in, const 
         }
         if (rc != 0) { status = 3; break; }
         if (dw > 0.0) dw_last = dw;
-        riccati_forward(cta, cfg, in, w, sm, false);
+        lin.forward(cta, cfg, in, w, false);
         recover_path(cta, cfg, in, w, mu, dc);
         costate_backward(cta, cfg, in, w, dw);
         // ---- iterative refinement on the stationarity residual of the Newton system (the eliminated rows hold exactly)
@@ -1104,8 +1115,8 @@ CMPC_HD Result ipm_solve(Cta& cta, const Config& cfg, const Instance& in, const 
             double rho = lin_residual(cta, cfg, in, w, dw);
             if (!(rho > REFINE_TOL) || rho > 0.5 * rho_prev) break;
             rho_prev = rho;
-            refine_backward(cta, cfg, w, sm);
-            riccati_forward(cta, cfg, in, w, sm, true);
+            lin.refine_back(cta, cfg, w);
+            lin.forward(cta, cfg, in, w, true);
             recover_path(cta, cfg, in, w, mu, dc);
             costate_backward(cta, cfg, in, w, dw);
         }

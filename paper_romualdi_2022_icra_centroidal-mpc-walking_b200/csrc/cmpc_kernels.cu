@@ -18,6 +18,7 @@
 
 #include "../../include/cmpc_b200.h"
 #include "cmpc_sparse.cuh"
+#include "cmpc_warp.cuh"
 
 namespace cmpc {
 
@@ -64,7 +65,67 @@ __device__ __forceinline__ DevCta make_cta(double* red)
     return c;
 }
 
+// one warp = one "CTA" of the solver: barriers are __syncwarp, reductions are shuffles (no shared memory, no block barrier)
+struct DevWarp {
+    int tid, nt, warp, lane, wsize;
+    __device__ __forceinline__ void sync() { __syncwarp(); }
+    __device__ __forceinline__ void syncwarp() { __syncwarp(); }
+    template <int K, class Op>
+    __device__ __forceinline__ void allreduce(double* v, Op op)
+    {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double x = v[k];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) x = op(x, __shfl_xor_sync(0xffffffffu, x, off));
+            v[k] = x;
+        }
+    }
+    template <int K> __device__ __forceinline__ void sumv(double* v) { allreduce<K>(v, [](double a, double b) { return a + b; }); }
+    template <int K> __device__ __forceinline__ void maxv(double* v) { allreduce<K>(v, [](double a, double b) { return fmax(a, b); }); }
+    template <int K> __device__ __forceinline__ void minv(double* v) { allreduce<K>(v, [](double a, double b) { return fmin(a, b); }); }
+    __device__ __forceinline__ double sum(double x) { sumv<1>(&x); return x; }
+    __device__ __forceinline__ double max(double x) { maxv<1>(&x); return x; }
+};
+
 // ------------------------------------------------------------------------------------------------ kernels
+#ifndef CMPC_WARPS_PER_SM
+#define CMPC_WARPS_PER_SM 7
+#endif
+
+// THE hot path: persistent one-warp CTAs, one MPC instance per warp at a time (atomic work queue).  The whole
+// interior-point solve of the instance runs inside the warp: Riccati factorisation in registers / shared memory
+// (cmpc_warp.cuh), iterate vectors in a per-warp scratch block that stays in L2.
+__global__ void __launch_bounds__(32, CMPC_WARPS_PER_SM)
+cmpc_solve_warp_kernel(Config cfg, int batch, const double* __restrict__ p, const double* __restrict__ lbg,
+                       const double* __restrict__ ubg, double* x, double* lam, double* obj, int* status, int* iters,
+                       int warm_duals, double* work, size_t work_stride, unsigned int* counter)
+{
+    extern __shared__ double smem_raw[];
+    WSmem& sm = *reinterpret_cast<WSmem*>(smem_raw);
+    DevWarp cta;
+    cta.tid = threadIdx.x; cta.nt = 32; cta.warp = 0; cta.lane = threadIdx.x; cta.wsize = 32;
+    const int N = cfg.N, n = dim_x(N), np = dim_p(N), m = dim_g(N);
+    double* base = work + (size_t)blockIdx.x * work_stride;
+    Work w;
+    work_carve(base, N, w);
+    LinWarp lin{sm, WorkW{base + work_doubles(N), base + work_doubles(N) + (N + 1) * SMALL_STRIDE}};
+    for (;;) {
+        int inst = 0;
+        if (threadIdx.x == 0) inst = (int)atomicAdd(counter, 1u);
+        inst = __shfl_sync(0xffffffffu, inst, 0);
+        if (inst >= batch) break;
+        Instance in{p + (size_t)inst * np, lbg + (size_t)inst * m, ubg + (size_t)inst * m};
+        Result r = ipm_solve(cta, cfg, in, w, lin, x + (size_t)inst * n, lam ? lam + (size_t)inst * m : nullptr, warm_duals);
+        if (threadIdx.x == 0) {
+            if (obj) obj[inst] = r.obj;
+            if (status) status[inst] = r.status;
+            if (iters) iters[inst] = r.iters;
+        }
+        __syncwarp();
+    }
+}
+
 #ifndef CMPC_MIN_CTAS
 #define CMPC_MIN_CTAS 3
 #endif
@@ -88,7 +149,8 @@ cmpc_solve_kernel(Config cfg, int batch, const double* __restrict__ p, const dou
         __syncthreads();
         if (inst >= batch) break;
         Instance in{p + (size_t)inst * np, lbg + (size_t)inst * m, ubg + (size_t)inst * m};
-        Result r = ipm_solve(cta, cfg, in, w, sm, x + (size_t)inst * n, lam ? lam + (size_t)inst * m : nullptr, warm_duals);
+        LinCta lin{sm};
+        Result r = ipm_solve(cta, cfg, in, w, lin, x + (size_t)inst * n, lam ? lam + (size_t)inst * m : nullptr, warm_duals);
         if (threadIdx.x == 0) {
             if (obj) obj[inst] = r.obj;
             if (status) status[inst] = r.status;
@@ -390,15 +452,23 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, h->device);
     if (e != cudaSuccess) { delete h; return CMPC_E_CUDA; }
     h->sm_count = prop.multiProcessorCount;
-    h->threads = 128;  // the kernel is compiled with __launch_bounds__(128, .)
-    h->smem = (int)sizeof(Smem);
-    e = cudaFuncSetAttribute(cmpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
+    // threads_per_instance: 0 / 32 = one warp per instance (the product path); 128 = the generic 4-warp CTA variant
+    if (u->threads_per_instance != 0 && u->threads_per_instance != 32 && u->threads_per_instance != 128) { delete h; return CMPC_E_INVALID; }
+    h->threads = u->threads_per_instance == 128 ? 128 : 32;
     int occ = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cmpc_solve_kernel, h->threads, h->smem);
+    if (h->threads == 128) {
+        h->smem = (int)sizeof(Smem);
+        e = cudaFuncSetAttribute(cmpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cmpc_solve_kernel, h->threads, h->smem);
+    } else {
+        h->smem = (int)sizeof(WSmem);
+        e = cudaFuncSetAttribute(cmpc_solve_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cmpc_solve_warp_kernel, h->threads, h->smem);
+    }
     if (e != cudaSuccess || occ < 1) { h->last_cuda = (int)e; delete h; return CMPC_E_CUDA; }
     h->ctas_per_sm = (u->ctas_per_sm > 0 && u->ctas_per_sm < occ) ? u->ctas_per_sm : occ;
     h->grid = h->sm_count * h->ctas_per_sm;  // persistent grid: a multiple of the SM count
-    h->work_stride = ((size_t)work_doubles(c.N) + 15) & ~(size_t)15;
+    h->work_stride = ((size_t)(work_doubles(c.N) + workw_doubles(c.N)) + 15) & ~(size_t)15;
     Csc jc, hc;
     build_csc(c.N, false, jc);
     build_csc(c.N, true, hc);
@@ -438,8 +508,12 @@ int cmpc_solve_batched(cmpc_handle h, int batch, const double* d_p, const double
     CK(cudaSetDevice(h->device));
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
     int grid = std::min(batch, h->grid);
-    cmpc_solve_kernel<<<grid, h->threads, h->smem, st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj, d_status,
-                                                         d_iters, warm_duals, h->d_work, h->work_stride, h->d_counter);
+    if (h->threads == 128)
+        cmpc_solve_kernel<<<grid, 128, h->smem, st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj, d_status,
+                                                      d_iters, warm_duals, h->d_work, h->work_stride, h->d_counter);
+    else
+        cmpc_solve_warp_kernel<<<grid, 32, h->smem, st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj, d_status,
+                                                          d_iters, warm_duals, h->d_work, h->work_stride, h->d_counter);
     h->launches++;
     CK(cudaGetLastError());
     return CMPC_OK;

@@ -7,7 +7,7 @@
 #include <cstring>
 #include <vector>
 
-#include "../../paper_romualdi_2022_icra_centroidal-mpc-walking_b200/csrc/cmpc_core.cuh"
+#include "../../paper_romualdi_2022_icra_centroidal-mpc-walking_b200/csrc/cmpc_warp.cuh"
 
 namespace {
 struct HostCta {
@@ -31,7 +31,25 @@ extern "C" int hostsim_solve(const cmpc::Config* cfg, const double* p, const dou
     cmpc::work_carve(buf.data(), cfg->N, w);
     static cmpc::Smem sm;
     cmpc::Instance in{p, lbg, ubg};
-    cmpc::Result r = cmpc::ipm_solve(cta, *cfg, in, w, sm, x, lam, warm_duals);
+    cmpc::LinCta lin{sm};
+    cmpc::Result r = cmpc::ipm_solve(cta, *cfg, in, w, lin, x, lam, warm_duals);
+    *iters = r.iters; *obj = r.obj; *kkt = r.kkt;
+    return r.status;
+}
+
+// the warp-per-instance sweeps (csrc/cmpc_warp.cuh) with 32 emulated lanes
+extern "C" int hostsim_solve_warp(const cmpc::Config* cfg, const double* p, const double* lbg, const double* ubg, double* x,
+                                  double* lam, int warm_duals, int* iters, double* obj, double* kkt)
+{
+    HostCta cta;
+    std::vector<double> buf(cmpc::work_doubles(cfg->N) + cmpc::workw_doubles(cfg->N), 0.0);
+    cmpc::Work w;
+    cmpc::work_carve(buf.data(), cfg->N, w);
+    static cmpc::WSmem sm;
+    cmpc::Instance in{p, lbg, ubg};
+    cmpc::LinWarp lin{sm, cmpc::WorkW{buf.data() + cmpc::work_doubles(cfg->N),
+                                      buf.data() + cmpc::work_doubles(cfg->N) + (cfg->N + 1) * cmpc::SMALL_STRIDE}};
+    cmpc::Result r = cmpc::ipm_solve(cta, *cfg, in, w, lin, x, lam, warm_duals);
     *iters = r.iters; *obj = r.obj; *kkt = r.kkt;
     return r.status;
 }
@@ -46,7 +64,8 @@ extern "C" int hostsim_dump(const cmpc::Config* cfg, const double* p, const doub
     cmpc::work_carve(buf.data(), cfg->N, w);
     static cmpc::Smem sm;
     cmpc::Instance in{p, lbg, ubg};
-    cmpc::Result r = cmpc::ipm_solve(cta, *cfg, in, w, sm, x, lam, 0);
+    cmpc::LinCta lin{sm};
+    cmpc::Result r = cmpc::ipm_solve(cta, *cfg, in, w, lin, x, lam, 0);
     const int q = 38 * cfg->N;
     std::memcpy(s, w.s, 8 * q); std::memcpy(zL, w.zL, 8 * q); std::memcpy(zU, w.zU, 8 * q);
     std::memcpy(sL, w.sL, 8 * q); std::memcpy(sU, w.sU, 8 * q);
