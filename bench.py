@@ -145,6 +145,7 @@ def main():
     ap.add_argument("--workload", default="icub3_b1024")
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--team", type=int, default=0, help="threads per instance (32/64/128), 0 = library default")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -167,6 +168,7 @@ def main():
     cfg, w, ocfg = workload(args.workload, pkg, wl, seed=rank)   # every rank its own shard of instances
     cfg.device = local
     cfg.ipopt_tolerance = args.tol
+    cfg.threads_per_instance = args.team
     solver = pkg.BatchedCentroidalMPC(cfg)
     B, N = w["p"].shape[0], cfg.horizon
     n, m, npar = solver.L.n, solver.L.m, solver.L.np

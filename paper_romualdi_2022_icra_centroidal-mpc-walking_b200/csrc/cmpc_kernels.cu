@@ -89,67 +89,36 @@ struct DevWarp {
 };
 
 // ------------------------------------------------------------------------------------------------ kernels
-#ifndef CMPC_WARPS_PER_SM
-#define CMPC_WARPS_PER_SM 7
-#endif
+// THE hot path: persistent CTAs of NT threads (a "team": 1, 2 or 4 warps), one MPC instance per team at a time (atomic work
+// queue).  The whole interior-point solve of the instance runs inside the team: Riccati factorisation on 3 x 3 tiles in
+// shared memory (cmpc_warp.cuh), iterate vectors in a per-team scratch block that stays in L2.
+template <int NT> struct TeamCta { using type = DevCta; };
+template <> struct TeamCta<32> { using type = DevWarp; };
 
-// THE hot path: persistent one-warp CTAs, one MPC instance per warp at a time (atomic work queue).  The whole
-// interior-point solve of the instance runs inside the warp: Riccati factorisation in registers / shared memory
-// (cmpc_warp.cuh), iterate vectors in a per-warp scratch block that stays in L2.
-__global__ void __launch_bounds__(32, CMPC_WARPS_PER_SM)
-cmpc_solve_warp_kernel(Config cfg, int batch, const double* __restrict__ p, const double* __restrict__ lbg,
-                       const double* __restrict__ ubg, double* x, double* lam, double* obj, int* status, int* iters,
-                       int warm_duals, double* work, size_t work_stride, unsigned int* counter)
+template <int NT, int CTAS>
+__global__ void __launch_bounds__(NT, CTAS)
+cmpc_solve_team_kernel(const __grid_constant__ Config cfg, int batch, const double* __restrict__ p,
+                       const double* __restrict__ lbg, const double* __restrict__ ubg, double* x, double* lam, double* obj,
+                       int* status, int* iters, int warm_duals, double* work, size_t work_stride, unsigned int* counter)
 {
     extern __shared__ double smem_raw[];
     WSmem& sm = *reinterpret_cast<WSmem*>(smem_raw);
-    DevWarp cta;
-    cta.tid = threadIdx.x; cta.nt = 32; cta.warp = 0; cta.lane = threadIdx.x; cta.wsize = 32;
+    __shared__ int s_inst;
+    typename TeamCta<NT>::type cta;
+    cta.tid = threadIdx.x; cta.nt = NT; cta.warp = threadIdx.x >> 5; cta.lane = threadIdx.x & 31; cta.wsize = 32;
+    if constexpr (NT != 32) cta.red = sm.red;
     const int N = cfg.N, n = dim_x(N), np = dim_p(N), m = dim_g(N);
     double* base = work + (size_t)blockIdx.x * work_stride;
     Work w;
     work_carve(base, N, w);
-    LinWarp lin{sm, WorkW{base + work_doubles(N), base + work_doubles(N) + (N + 1) * SMALL_STRIDE}};
-    for (;;) {
-        int inst = 0;
-        if (threadIdx.x == 0) inst = (int)atomicAdd(counter, 1u);
-        inst = __shfl_sync(0xffffffffu, inst, 0);
-        if (inst >= batch) break;
-        Instance in{p + (size_t)inst * np, lbg + (size_t)inst * m, ubg + (size_t)inst * m};
-        Result r = ipm_solve(cta, cfg, in, w, lin, x + (size_t)inst * n, lam ? lam + (size_t)inst * m : nullptr, warm_duals);
-        if (threadIdx.x == 0) {
-            if (obj) obj[inst] = r.obj;
-            if (status) status[inst] = r.status;
-            if (iters) iters[inst] = r.iters;
-        }
-        __syncwarp();
-    }
-}
-
-#ifndef CMPC_MIN_CTAS
-#define CMPC_MIN_CTAS 3
-#endif
-
-__global__ void __launch_bounds__(128, CMPC_MIN_CTAS)
-cmpc_solve_kernel(Config cfg, int batch, const double* __restrict__ p, const double* __restrict__ lbg,
-                  const double* __restrict__ ubg, double* x, double* lam, double* obj, int* status, int* iters,
-                  int warm_duals, double* work, size_t work_stride, unsigned int* counter)
-{
-    extern __shared__ double smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-    __shared__ int s_inst;
-    DevCta cta = make_cta(sm.red);
-    const int N = cfg.N, n = dim_x(N), np = dim_p(N), m = dim_g(N);
-    Work w;
-    work_carve(work + (size_t)blockIdx.x * work_stride, N, w);
+    LinTeam<NT> lin{sm, WorkW{base + work_doubles(N), base + work_doubles(N) + (N + 1) * SMALL_STRIDE}};
     for (;;) {
         if (threadIdx.x == 0) s_inst = (int)atomicAdd(counter, 1u);
-        __syncthreads();
+        team_sync<NT>();
         const int inst = s_inst;
-        __syncthreads();
+        team_sync<NT>();
         if (inst >= batch) break;
         Instance in{p + (size_t)inst * np, lbg + (size_t)inst * m, ubg + (size_t)inst * m};
-        LinCta lin{sm};
         Result r = ipm_solve(cta, cfg, in, w, lin, x + (size_t)inst * n, lam ? lam + (size_t)inst * m : nullptr, warm_duals);
         if (threadIdx.x == 0) {
             if (obj) obj[inst] = r.obj;
@@ -344,10 +313,20 @@ static void build_csc(int N, bool hess, Csc& out)
 
 using namespace cmpc;
 
+#ifndef CMPC_DEFAULT_TEAM
+#define CMPC_DEFAULT_TEAM 128
+#endif
+static const void* team_kernel(int nt)
+{
+    if (nt == 32) return (const void*)cmpc_solve_team_kernel<32, 6>;
+    if (nt == 64) return (const void*)cmpc_solve_team_kernel<64, 6>;
+    return (const void*)cmpc_solve_team_kernel<128, 6>;
+}
+
 struct cmpc_handle_s {
     Config cfg;
     cmpc_config user;
-    int device = 0, sm_count = 0, threads = 128, ctas_per_sm = 0, grid = 0, smem = 0;
+    int device = 0, sm_count = 0, threads = CMPC_DEFAULT_TEAM, ctas_per_sm = 0, grid = 0, smem = 0;
     size_t work_stride = 0;
     double* d_work = nullptr;
     unsigned int* d_counter = nullptr;
@@ -452,19 +431,14 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, h->device);
     if (e != cudaSuccess) { delete h; return CMPC_E_CUDA; }
     h->sm_count = prop.multiProcessorCount;
-    // threads_per_instance: 0 / 32 = one warp per instance (the product path); 128 = the generic 4-warp CTA variant
-    if (u->threads_per_instance != 0 && u->threads_per_instance != 32 && u->threads_per_instance != 128) { delete h; return CMPC_E_INVALID; }
-    h->threads = u->threads_per_instance == 128 ? 128 : 32;
+    // threads_per_instance: team size, 32 / 64 / 128 (0 = default)
+    h->threads = u->threads_per_instance == 0 ? CMPC_DEFAULT_TEAM : u->threads_per_instance;
+    if (h->threads != 32 && h->threads != 64 && h->threads != 128) { delete h; return CMPC_E_INVALID; }
+    h->smem = (int)sizeof(WSmem);
+    const void* kfn = team_kernel(h->threads);
     int occ = 0;
-    if (h->threads == 128) {
-        h->smem = (int)sizeof(Smem);
-        e = cudaFuncSetAttribute(cmpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cmpc_solve_kernel, h->threads, h->smem);
-    } else {
-        h->smem = (int)sizeof(WSmem);
-        e = cudaFuncSetAttribute(cmpc_solve_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cmpc_solve_warp_kernel, h->threads, h->smem);
-    }
+    e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, h->threads, h->smem);
     if (e != cudaSuccess || occ < 1) { h->last_cuda = (int)e; delete h; return CMPC_E_CUDA; }
     h->ctas_per_sm = (u->ctas_per_sm > 0 && u->ctas_per_sm < occ) ? u->ctas_per_sm : occ;
     h->grid = h->sm_count * h->ctas_per_sm;  // persistent grid: a multiple of the SM count
@@ -508,12 +482,15 @@ int cmpc_solve_batched(cmpc_handle h, int batch, const double* d_p, const double
     CK(cudaSetDevice(h->device));
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
     int grid = std::min(batch, h->grid);
-    if (h->threads == 128)
-        cmpc_solve_kernel<<<grid, 128, h->smem, st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj, d_status,
-                                                      d_iters, warm_duals, h->d_work, h->work_stride, h->d_counter);
+    if (h->threads == 32)
+        cmpc_solve_team_kernel<32, 6><<<grid, 32, h->smem, st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj, d_status,
+                                                                 d_iters, warm_duals, h->d_work, h->work_stride, h->d_counter);
+    else if (h->threads == 64)
+        cmpc_solve_team_kernel<64, 6><<<grid, 64, h->smem, st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj, d_status,
+                                                                 d_iters, warm_duals, h->d_work, h->work_stride, h->d_counter);
     else
-        cmpc_solve_warp_kernel<<<grid, 32, h->smem, st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj, d_status,
-                                                          d_iters, warm_duals, h->d_work, h->work_stride, h->d_counter);
+        cmpc_solve_team_kernel<128, 6><<<grid, 128, h->smem, st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj, d_status,
+                                                                   d_iters, warm_duals, h->d_work, h->work_stride, h->d_counter);
     h->launches++;
     CK(cudaGetLastError());
     return CMPC_OK;

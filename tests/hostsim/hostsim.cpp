@@ -37,9 +37,10 @@ extern "C" int hostsim_solve(const cmpc::Config* cfg, const double* p, const dou
     return r.status;
 }
 
-// the warp-per-instance sweeps (csrc/cmpc_warp.cuh) with 32 emulated lanes
-extern "C" int hostsim_solve_warp(const cmpc::Config* cfg, const double* p, const double* lbg, const double* ubg, double* x,
-                                  double* lam, int warm_duals, int* iters, double* obj, double* kkt)
+// the team sweeps (csrc/cmpc_warp.cuh) with NT emulated threads
+template <int NT>
+static int solve_team(const cmpc::Config* cfg, const double* p, const double* lbg, const double* ubg, double* x, double* lam,
+                      int warm_duals, int* iters, double* obj, double* kkt)
 {
     HostCta cta;
     std::vector<double> buf(cmpc::work_doubles(cfg->N) + cmpc::workw_doubles(cfg->N), 0.0);
@@ -47,12 +48,18 @@ extern "C" int hostsim_solve_warp(const cmpc::Config* cfg, const double* p, cons
     cmpc::work_carve(buf.data(), cfg->N, w);
     static cmpc::WSmem sm;
     cmpc::Instance in{p, lbg, ubg};
-    cmpc::LinWarp lin{sm, cmpc::WorkW{buf.data() + cmpc::work_doubles(cfg->N),
-                                      buf.data() + cmpc::work_doubles(cfg->N) + (cfg->N + 1) * cmpc::SMALL_STRIDE}};
+    cmpc::LinTeam<NT> lin{sm, cmpc::WorkW{buf.data() + cmpc::work_doubles(cfg->N),
+                                          buf.data() + cmpc::work_doubles(cfg->N) + (cfg->N + 1) * cmpc::SMALL_STRIDE}};
     cmpc::Result r = cmpc::ipm_solve(cta, *cfg, in, w, lin, x, lam, warm_duals);
     *iters = r.iters; *obj = r.obj; *kkt = r.kkt;
     return r.status;
 }
+extern "C" int hostsim_solve_team32(const cmpc::Config* cfg, const double* p, const double* lbg, const double* ubg, double* x,
+                                    double* lam, int warm_duals, int* iters, double* obj, double* kkt)
+{ return solve_team<32>(cfg, p, lbg, ubg, x, lam, warm_duals, iters, obj, kkt); }
+extern "C" int hostsim_solve_team128(const cmpc::Config* cfg, const double* p, const double* lbg, const double* ubg, double* x,
+                                     double* lam, int warm_duals, int* iters, double* obj, double* kkt)
+{ return solve_team<128>(cfg, p, lbg, ubg, x, lam, warm_duals, iters, obj, kkt); }
 
 // debug: run `max_iter` iterations and export the internal state and the last search direction
 extern "C" int hostsim_dump(const cmpc::Config* cfg, const double* p, const double* lbg, const double* ubg, double* x,
