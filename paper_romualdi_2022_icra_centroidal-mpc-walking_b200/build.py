@@ -38,7 +38,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.run(cmd, check=True)
     host_src = [s for s in HOST_SOURCES if os.path.exists(s)]
-    if host_src and (force or _stale(HOSTLIB, host_src + [os.path.join(HERE, "host", f) for f in os.listdir(os.path.join(HERE, "host"))])):
+    hdir = os.path.join(HERE, "host", "BipedalLocomotion")
+    hdeps = host_src + ([os.path.join(hdir, f) for f in os.listdir(hdir)] if os.path.isdir(hdir) else []) + [LIB]
+    if host_src and (force or _stale(HOSTLIB, hdeps)):
         inc = os.path.join(os.path.dirname(HERE), "include")
         cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", inc, "-I", os.path.join(HERE, "host"), *host_src, "-o", HOSTLIB,
                "-L", HERE, "-lcmpc_b200", "-Wl,-rpath,$ORIGIN"]

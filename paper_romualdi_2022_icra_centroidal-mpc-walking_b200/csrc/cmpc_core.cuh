@@ -25,6 +25,12 @@
 #endif
 
 namespace cmpc {
+#ifdef CMPC_HOST_STATS
+static long g_stat[8];  // backward sweeps, refinements, line-search trials, iterations, mu updates
+#define CMPC_STAT(i) (++g_stat[i])
+#else
+#define CMPC_STAT(i) ((void)0)
+#endif
 
 // ------------------------------------------------------------------------------------------------ data
 struct Config {
@@ -1068,11 +1074,13 @@ CMPC_HD Result ipm_solve(Cta& cta, const Config& cfg, const Instance& in, const 
         for (;;) {
             Errs em = kkt_error(cta, cfg, in, w, mu);
             if (em.E <= KAPPA_EPS * mu && mu > mu_min) {
+                CMPC_STAT(4);
                 mu = fmax(mu_min, fmin(KAPPA_MU * mu, mu * sqrt(mu)));
                 tau = fmax(TAU_MIN, 1.0 - mu);
                 nfilt = 0;
             } else break;
         }
+        CMPC_STAT(3);
         // ---- search direction with inertia correction (alg. IC): Cholesky failure inside the Riccati sweep <=> wrong inertia
         const double dc = fmax(DC_BAR * sqrt(sqrt(mu)), DC_FLOOR);
         double dw = 0.0;
@@ -1098,6 +1106,7 @@ CMPC_HD Result ipm_solve(Cta& cta, const Config& cfg, const Instance& in, const 
                 w.sig[pr] = sg; w.tt[pr] = t;
             }
             cta.sync();
+            CMPC_STAT(0);
             rc = lin.backward(cta, cfg, in, w, dw);
             if (rc == 0) break;
             if (dw == 0.0) dw = dw_last == 0.0 ? DW_FIRST : fmax(DW_MIN, KW_MINUS * dw_last);
@@ -1115,6 +1124,7 @@ CMPC_HD Result ipm_solve(Cta& cta, const Config& cfg, const Instance& in, const 
             double rho = lin_residual(cta, cfg, in, w, dw);
             if (!(rho > REFINE_TOL) || rho > 0.5 * rho_prev) break;
             rho_prev = rho;
+            CMPC_STAT(1);
             lin.refine_back(cta, cfg, w);
             lin.forward(cta, cfg, in, w, true);
             recover_path(cta, cfg, in, w, mu, dc);
@@ -1168,6 +1178,7 @@ CMPC_HD Result ipm_solve(Cta& cta, const Config& cfg, const Instance& in, const 
             for (int i = cta.tid; i < n; i += cta.nt) w.xt[i] = w.x[i] + alpha * w.dx[i];
             for (int pr = cta.tid; pr < npr; pr += cta.nt) w.st[pr] = w.s[pr] + alpha * w.ds[pr];
             cta.sync();
+            CMPC_STAT(2);
             stage_data(cta, cfg, in, w.xt, w.sd);
             eval_g(cta, cfg, in, w.xt, w.sd, w.g);
             ft = eval_f(cta, cfg, in, w.xt, (double*)nullptr);

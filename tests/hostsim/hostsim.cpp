@@ -80,4 +80,7 @@ extern "C" int hostsim_dump(const cmpc::Config* cfg, const double* p, const doub
     return r.status;
 }
 
+#ifdef CMPC_HOST_STATS
+extern "C" void hostsim_stats(long* out) { for (int i = 0; i < 8; ++i) { out[i] = cmpc::g_stat[i]; cmpc::g_stat[i] = 0; } }
+#endif
 extern "C" int hostsim_config_size() { return (int)sizeof(cmpc::Config); }
