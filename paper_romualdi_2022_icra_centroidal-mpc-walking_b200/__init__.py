@@ -60,6 +60,7 @@ def load_library() -> C.CDLL:
     L.cmpc_eval_jac_fg.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, vp]
     L.cmpc_eval_hess_l.argtypes = [vp, i, vp, vp, d, vp, vp, vp]
     L.cmpc_rollout_plant.argtypes = [vp, i, vp, vp, vp, vp, d, i, vp]
+    L.cmpc_measure_fp64_peak.argtypes = [vp, _dp]
     L.cmpc_launch_count.argtypes = [vp]
     L.cmpc_launch_count.restype = C.c_longlong
     L.cmpc_last_cuda_error.argtypes = [vp]
@@ -146,6 +147,11 @@ class BatchedCentroidalMPC:
         v = [C.c_int() for _ in range(5)]
         self.lib.cmpc_solver_geometry(self.handle, *[C.byref(a) for a in v])
         return dict(grid=v[0].value, threads=v[1].value, smem=v[2].value, ctas_per_sm=v[3].value, sm_count=v[4].value)
+
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double()
+        _check(self.lib.cmpc_measure_fp64_peak(self.handle, C.byref(v)), "cmpc_measure_fp64_peak", self.handle)
+        return v.value
 
     def launch_count(self) -> int:
         return int(self.lib.cmpc_launch_count(self.handle))

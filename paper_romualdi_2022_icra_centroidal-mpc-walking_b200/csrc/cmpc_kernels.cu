@@ -1,8 +1,8 @@
 // cmpc_kernels.cu -- sm_100a kernels and the C ABI (include/cmpc_b200.h) of the batched centroidal-MPC solve.
 //
 // Kernel inventory (see DESIGN.md for the roofline of each):
-//   cmpc_solve_kernel     persistent CTAs, one MPC instance per CTA at a time (atomic work queue): the whole
-//                         interior-point solve incl. the per-knot Riccati factorisation in shared memory
+//   cmpc_solve_team_kernel  persistent CTAs, one MPC instance per team of 32/64/128 threads at a time (atomic work queue):
+//                         the whole interior-point solve incl. the per-knot Riccati factorisation in shared memory
 //   cmpc_shift_kernel     warm-start shift of x / lam_g by one knot (HBM bound, coalesced, staged in shared memory)
 //   cmpc_eval_kernel      f, grad f, g of the NLP (parity surface for nlp_fg / nlp_jac_fg)
 //   cmpc_jac_kernel / cmpc_hess_kernel   entry-wise CSC jacobian / hessian (parity surface)
@@ -266,6 +266,17 @@ __global__ void cmpc_plant_kernel(Config cfg, int batch, const double* __restric
     }
 }
 
+// FP64 FMA throughput probe: 8 independent DFMA chains per thread, no memory traffic (roofline denominator of bench.py)
+__global__ void cmpc_dfma_probe_kernel(double* out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    if (x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7 == 123.456) out[0] = x0;  // keeps the chains alive, never true in practice
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static void friction_matrix_host(double mu, double A[NF][3])
 {
@@ -316,11 +327,15 @@ using namespace cmpc;
 #ifndef CMPC_DEFAULT_TEAM
 #define CMPC_DEFAULT_TEAM 128
 #endif
+#ifndef CMPC_CTAS_PER_SM
+#define CMPC_CTAS_PER_SM 7
+#endif
 static const void* team_kernel(int nt)
 {
-    if (nt == 32) return (const void*)cmpc_solve_team_kernel<32, 6>;
-    if (nt == 64) return (const void*)cmpc_solve_team_kernel<64, 6>;
-    return (const void*)cmpc_solve_team_kernel<128, 6>;
+    if (nt == 32) return (const void*)cmpc_solve_team_kernel<32, CMPC_CTAS_PER_SM>;
+    if (nt == 64) return (const void*)cmpc_solve_team_kernel<64, CMPC_CTAS_PER_SM>;
+    if (nt == 96) return (const void*)cmpc_solve_team_kernel<96, CMPC_CTAS_PER_SM>;
+    return (const void*)cmpc_solve_team_kernel<128, CMPC_CTAS_PER_SM>;
 }
 
 struct cmpc_handle_s {
@@ -433,7 +448,7 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
     h->sm_count = prop.multiProcessorCount;
     // threads_per_instance: team size, 32 / 64 / 128 (0 = default)
     h->threads = u->threads_per_instance == 0 ? CMPC_DEFAULT_TEAM : u->threads_per_instance;
-    if (h->threads != 32 && h->threads != 64 && h->threads != 128) { delete h; return CMPC_E_INVALID; }
+    if (h->threads != 32 && h->threads != 64 && h->threads != 96 && h->threads != 128) { delete h; return CMPC_E_INVALID; }
     h->smem = (int)sizeof(WSmem);
     const void* kfn = team_kernel(h->threads);
     int occ = 0;
@@ -482,15 +497,15 @@ int cmpc_solve_batched(cmpc_handle h, int batch, const double* d_p, const double
     CK(cudaSetDevice(h->device));
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
     int grid = std::min(batch, h->grid);
-    if (h->threads == 32)
-        cmpc_solve_team_kernel<32, 6><<<grid, 32, h->smem, st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj, d_status,
-                                                                 d_iters, warm_duals, h->d_work, h->work_stride, h->d_counter);
-    else if (h->threads == 64)
-        cmpc_solve_team_kernel<64, 6><<<grid, 64, h->smem, st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj, d_status,
-                                                                 d_iters, warm_duals, h->d_work, h->work_stride, h->d_counter);
-    else
-        cmpc_solve_team_kernel<128, 6><<<grid, 128, h->smem, st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj, d_status,
-                                                                   d_iters, warm_duals, h->d_work, h->work_stride, h->d_counter);
+#define CMPC_LAUNCH_TEAM(NT)                                                                                                  \
+    cmpc_solve_team_kernel<NT, CMPC_CTAS_PER_SM><<<grid, NT, h->smem, st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj, \
+                                                                            d_status, d_iters, warm_duals, h->d_work,        \
+                                                                            h->work_stride, h->d_counter)
+    if (h->threads == 32) CMPC_LAUNCH_TEAM(32);
+    else if (h->threads == 64) CMPC_LAUNCH_TEAM(64);
+    else if (h->threads == 96) CMPC_LAUNCH_TEAM(96);
+    else CMPC_LAUNCH_TEAM(128);
+#undef CMPC_LAUNCH_TEAM
     h->launches++;
     CK(cudaGetLastError());
     return CMPC_OK;
@@ -610,6 +625,31 @@ int cmpc_rollout_plant(cmpc_handle h, int batch, const double* d_x, const double
     cmpc_plant_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(h->cfg, batch, d_x, d_p, d_ext, d_state, dt, substeps);
     h->launches++;
     CK(cudaGetLastError());
+    return CMPC_OK;
+}
+
+int cmpc_measure_fp64_peak(cmpc_handle h, double* tflops)
+{
+    if (!h || !tflops) return CMPC_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    const int iters = 1 << 16, threads = 256, blocks = h->sm_count * 8;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {  // first repetition is the warm-up
+        CK(cudaEventRecord(e0, 0));
+        cmpc_dfma_probe_kernel<<<blocks, threads>>>(h->d_gscratch, iters, 0.999999, 1e-9);
+        CK(cudaEventRecord(e1, 0));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = 2.0 * 8.0 * iters * (double)threads * blocks / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
     return CMPC_OK;
 }
 
