@@ -1,0 +1,837 @@
+// cmpc_ipm.cuh -- the interior-point solve of one centroidal-MPC instance by one team of NT threads, STAGE MAJOR.
+//
+// Same algorithm as ipm_solve() of cmpc_core.cuh (IPOPT's filter line-search interior point, Waechter & Biegler 2006, the
+// restatement of what BLF CentroidalMPC::advance() delegates to CasADi + IPOPT at
+// /root/reference/src/centroidal-mpc-walking/src/CentroidalMPCBlock.cpp:615), re-organised for the GPU:
+//   * every per-instance vector lives knot by knot (z_k = [s_k | u_k], the 15 equality rows that define s_k, the 38 path rows
+//     of knot k), padded so that an item (knot, role) is a shift and a mask away from the thread index: no divisions, no
+//     CasADi-order index arithmetic inside the iterations (the CasADi order exists only at entry and exit);
+//   * per-knot constants (rotations, friction rows A R', corner offsets R r_j, references, ...) are tabulated once per solve;
+//   * the element-wise work of an iteration is fused into a few passes over (knot, role) items: one KKT pass (gradient, dual /
+//     primal / complementarity residuals; the barrier-parameter loop needs no second pass because max |s z - mu| follows from
+//     max and min of the products), one barrier pass (Sigma, barrier gradients, the small blocks of the Riccati sweep), one
+//     step pass (eliminated rows, fraction to the boundary, directional derivative), one evaluation pass per trial point;
+//   * the adjoint recursion for the dynamics multipliers is a 16-step shuffle chain on one warp.
+// The linear algebra (Riccati sweeps on 3 x 3 tiles) is in cmpc_warp.cuh.
+#pragma once
+
+#include "cmpc_warp.cuh"
+
+namespace cmpc {
+
+constexpr int PS = 40;  // stride of a knot in the path-row arrays: friction 0..31 (16 c + 4 j + r) | step box 32..37 (32 + 3 c + q) | pad
+// per-knot table of constants
+constexpr int TS = 100;
+constexpr int T_EN = 0, T_OMD = 2, T_VM = 4, T_AR = 8, T_R = 32, T_RR = 50, T_NOM = 74, T_NOM1 = 80, T_CREF = 86, T_HREF = 89,
+              T_EXTF = 92, T_EXTT = 95, T_OM2 = 98;
+constexpr int AWS = 32;  // stride of the per-knot values of the off-diagonal non-zeros of A (15 x 2)
+
+struct WorkS {
+    double *z, *dz, *zt, *gr, *res;                                                   // (N + 1) * ZS
+    double *lam, *dlam, *ceq, *lamn, *vco, *beq;                                      // (N + 1) * ES
+    double *gp, *sl, *slt, *zl, *zu, *lo, *up, *yp, *ypn, *sig, *tt, *dsl, *dzl, *dzu, *dyp;  // N * PS
+    double *tab;                                                                      // (N + 1) * TS
+    double *sd, *aw, *dfc;                                                            // N * SD_STRIDE, N * AWS, N * 8
+    double *small;                                                                    // (N + 1) * SMALL_STRIDE
+    double *ric;                                                                      // N * WRIC_STRIDE
+};
+CMPC_HD int works_doubles(int N)
+{
+    return 5 * (N + 1) * ZS + 6 * (N + 1) * ES + 15 * N * PS + (N + 1) * TS + N * (SD_STRIDE + AWS + 8) + (N + 1) * SMALL_STRIDE
+           + N * WRIC_STRIDE;
+}
+CMPC_HD void works_carve(double* base, int N, WorkS& w)
+{
+    double* c = base;
+    const int nz = (N + 1) * ZS, ne = (N + 1) * ES, np = N * PS;
+    w.z = c; c += nz; w.dz = c; c += nz; w.zt = c; c += nz; w.gr = c; c += nz; w.res = c; c += nz;
+    w.lam = c; c += ne; w.dlam = c; c += ne; w.ceq = c; c += ne; w.lamn = c; c += ne; w.vco = c; c += ne; w.beq = c; c += ne;
+    w.gp = c; c += np; w.sl = c; c += np; w.slt = c; c += np; w.zl = c; c += np; w.zu = c; c += np; w.lo = c; c += np;
+    w.up = c; c += np; w.yp = c; c += np; w.ypn = c; c += np; w.sig = c; c += np; w.tt = c; c += np; w.dsl = c; c += np;
+    w.dzl = c; c += np; w.dzu = c; c += np; w.dyp = c; c += np;
+    w.tab = c; c += (N + 1) * TS;
+    w.sd = c; c += N * SD_STRIDE; w.aw = c; c += N * AWS; w.dfc = c; c += N * 8;
+    w.small = c; c += (N + 1) * SMALL_STRIDE;
+    w.ric = c;
+}
+
+// CasADi row of path row l of knot k
+CMPC_HD int path_row(int N, int k, int l)
+{
+    if (l < 32) return g_fric(N, l >> 4, (l >> 2) & 3, k) + (l & 3);
+    const int q = l - 32;
+    return g_box(N, q / 3, k) + q % 3;
+}
+// value  a' v  of path row l of knot k for variables taken from zk (knot k) / zk1 (knot k + 1); sub = 1 subtracts the nominal
+// position (row value), sub = 0 gives the jacobian row applied to a step
+CMPC_HD double path_dot(const double* tab, const double* zk, const double* zk1, int l, int sub)
+{
+    if (l < 32) {
+        const int c = l >> 4, j = (l >> 2) & 3, r = l & 3;
+        const double* ar = tab + T_AR + 12 * c + 3 * r;
+        const double* f = zk + NS + 6 + 12 * c + 3 * j;
+        return ar[0] * f[0] + ar[1] * f[1] + ar[2] * f[2];
+    }
+    const int q = l - 32, c = q / 3, qq = q - 3 * c;
+    const double* rc = tab + T_R + 9 * c + 3 * qq;  // column qq of R_c
+    const double* pos = zk1 + 9 + 3 * c;
+    const double* nom = tab + T_NOM1 + 3 * c;
+    double v = 0.0;
+    for (int a = 0; a < 3; ++a) v += rc[a] * (pos[a] - (sub ? nom[a] : 0.0));
+    return v;
+}
+
+// gradient of the objective in variable v (0..44) of knot k at the point zsrc
+CMPC_HD double grad_entry(const Config& cfg, const WorkS& w, const double* zsrc, int k, int v)
+{
+    const int N = cfg.N;
+    const double* t = w.tab + k * TS;
+    const double* zk = zsrc + k * ZS;
+    if (v < NS) {
+        if (v < 2) return 2.0 * cfg.w_com[v] * (zk[v] - t[T_CREF + v]);
+        if (v == 2) return 2.0 * t[T_OM2] * (zk[2] - t[T_CREF + 2]);
+        if (v < 6) return 0.0;
+        if (v < 9) return 2.0 * cfg.w_h * (zk[v] - t[T_HREF + v - 6]);
+        return 2.0 * cfg.w_pos * (zk[v] - t[T_NOM + v - 9]);
+    }
+    const int u = v - NS;
+    if (u < 6) return 0.0;
+    const int f = u - 6, c = f / 12, a = f % 3;
+    const double en = t[T_EN + c];
+    const double* fc = zk + NS + 6 + 12 * c + a;  // corner j at fc[3 j]
+    const double own = zk[v], sum = fc[0] + fc[3] + fc[6] + fc[9], mean = en / NJ * sum, d = own - mean;
+    double g = 2.0 * cfg.w_sym * (d - (en / NJ) * (sum - NJ * mean));
+    if (k + 1 < N) g -= 2.0 * cfg.w_rate[a] * (zsrc[(k + 1) * ZS + v] - own);
+    if (k > 0) g += 2.0 * cfg.w_rate[a] * (own - zsrc[(k - 1) * ZS + v]);
+    return g;
+}
+
+// (J' y)[variable v of knot k] for multipliers lam (equality rows, stage major) and yp (path rows); needs sd / aw at the iterate
+CMPC_HD double jty_entry(const Config& cfg, const WorkS& w, const double* lam, const double* yp, int k, int v)
+{
+    const int N = cfg.N;
+    if (v < NS) {
+        const int i = v;
+        double r = lam[k * ES + i];
+        if (k < N) {
+            const double* y1 = lam + (k + 1) * ES;
+            int rr[2];
+            acol_rows(i, rr);
+            r -= y1[i] + w.aw[k * AWS + 2 * i] * y1[rr[0]] + w.aw[k * AWS + 2 * i + 1] * y1[rr[1]];
+        }
+        if (k > 0 && i >= 9) {
+            const int c = (i - 9) / 3, a = (i - 9) % 3;
+            const double* R = w.tab + (k - 1) * TS + T_R + 9 * c;
+            const double* yb = yp + (k - 1) * PS + 32 + 3 * c;
+            r += R[a] * yb[0] + R[3 + a] * yb[1] + R[6 + a] * yb[2];
+        }
+        return r;
+    }
+    const int u = v - NS;
+    const double* t = w.tab + k * TS;
+    const double* y1 = lam + (k + 1) * ES;
+    if (u < 6) return -t[T_OMD + u / 3] * y1[9 + u];
+    const int f = u - 6, c = f / 12, j = (f % 12) / 3, a = f % 3, a1 = (a + 1) % 3, a2 = (a + 2) % 3;
+    const double* rho = w.sd + k * SD_STRIDE + SD_RHO + 3 * (4 * c + j);
+    double r = -cfg.dT * t[T_EN + c] * (y1[3 + a] + y1[6 + a1] * rho[a2] - y1[6 + a2] * rho[a1]);
+    const double* ar = t + T_AR + 12 * c + a;  // row q at ar[3 q]
+    const double* yf = yp + k * PS + 16 * c + 4 * j;
+    r += ar[0] * yf[0] + ar[3] * yf[1] + ar[6] * yf[2] + ar[9] * yf[3];
+    return r;
+}
+
+// (W dz)[variable v of knot k]: hessian of the lagrangian (nlp_hess_l, tmp.c:58926) + delta_w I, times the step
+CMPC_HD double hess_dz_entry(const Config& cfg, const WorkS& w, double dw, int k, int v)
+{
+    const int N = cfg.N;
+    const double* t = w.tab + k * TS;
+    const double* dzk = w.dz + k * ZS;
+    if (v < NS) {
+        const int i = v;
+        double q = i < 2 ? 2.0 * cfg.w_com[i] : i == 2 ? 2.0 * t[T_OM2] : i < 6 ? 0.0 : i < 9 ? 2.0 * cfg.w_h : 2.0 * cfg.w_pos;
+        double r = (q + dw) * dzk[i];
+        if (k < N && (i < 3 || i >= 9)) {  // bilinear block between forces and com / pos: dT en [lam_h]x
+            const double* lamh = w.lam + (k + 1) * ES + 6;
+            const int a = i < 3 ? i : (i - 9) % 3, a1 = (a + 1) % 3, a2 = (a + 2) % 3;
+            const double* dF = w.dfc + k * 8;
+            double acc;
+            if (i < 3) acc = t[T_EN] * (dF[a1] * lamh[a2] - dF[a2] * lamh[a1]) + t[T_EN + 1] * (dF[3 + a1] * lamh[a2] - dF[3 + a2] * lamh[a1]);
+            else { const int c = (i - 9) / 3; acc = -t[T_EN + c] * (dF[3 * c + a1] * lamh[a2] - dF[3 * c + a2] * lamh[a1]); }
+            r += cfg.dT * acc;
+        }
+        return r;
+    }
+    const int u = v - NS;
+    if (u < 6) return t[T_VM + u / 3] != 0.0 ? dzk[v] : dw * dzk[v];
+    const int f = u - 6, c = f / 12, a = f % 3, a1 = (a + 1) % 3, a2 = (a + 2) % 3;
+    const double a4 = t[T_EN + c] / NJ, own = dzk[v];
+    const double* dc = dzk + NS + 6 + 12 * c + a;
+    const double sum = dc[0] + dc[3] + dc[6] + dc[9];
+    double r = 2.0 * cfg.w_sym * (own + (NJ * a4 * a4 - 2.0 * a4) * sum) + dw * own;
+    if (k > 0) r += 2.0 * cfg.w_rate[a] * (own - w.dz[(k - 1) * ZS + v]);
+    if (k + 1 < N) r += 2.0 * cfg.w_rate[a] * (own - w.dz[(k + 1) * ZS + v]);
+    const double* lamh = w.lam + (k + 1) * ES + 6;
+    const double e1 = dzk[a1] - dzk[9 + 3 * c + a1], e2 = dzk[a2] - dzk[9 + 3 * c + a2];
+    r += cfg.dT * t[T_EN + c] * (lamh[a1] * e2 - lamh[a2] * e1);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------ evaluation of a point
+// stage data, equality residuals, path row values, objective, theta (l1 infeasibility) and the barrier function at (zsrc, slsrc)
+template <int NT, class Cta>
+CMPC_FN void eval_point(Cta& cta, const Config& cfg, const WorkS& w, const double* zsrc, const double* slsrc, double mu, double& f,
+                        double& theta, double& phi)
+{
+    const int N = cfg.N;
+    const double dT = cfg.dT;
+    CMPC_LANES
+        for (int it = lane; it < N * 32; it += NT) {
+            const int k = it >> 5, r = it & 31;
+            const double* t = w.tab + k * TS;
+            const double* zk = zsrc + k * ZS;
+            double* d = w.sd + k * SD_STRIDE;
+            if (r < 24) {
+                const int c = r >= 12 ? 1 : 0, a = (r - 12 * c) % 3;
+                d[SD_RHO + r] = t[T_RR + r] + zk[9 + 3 * c + a] - zk[a];
+            } else if (r < 30) {
+                const int q = r - 24, c = q / 3, a = q - 3 * c;
+                const double* fc = zk + NS + 6 + 12 * c + a;
+                d[SD_FC + q] = fc[0] + fc[3] + fc[6] + fc[9];
+            } else {
+                d[SD_EN + r - 30] = t[T_EN + r - 30];
+                d[SD_VM + r - 30] = t[T_VM + r - 30];
+            }
+        }
+    CMPC_LANES_END
+    double acc[3] = {0.0, 0.0, 0.0};  // f, theta, barrier terms
+    CMPC_LANES
+        for (int it = lane; it < (N + 1) * 64; it += NT) {
+            const int k = it >> 6, r = it & 63;
+            const double* t = w.tab + k * TS;
+            const double* zk = zsrc + k * ZS;
+            if (r < NS) {
+                // equality row block k: the rows that define s_k (k = 0: initial condition, k >= 1: dynamics of knot k - 1)
+                double c;
+                if (k == 0) c = zk[r];
+                else {
+                    const double* zp = zsrc + (k - 1) * ZS;
+                    const double* tp = w.tab + (k - 1) * TS;
+                    const double* d = w.sd + (k - 1) * SD_STRIDE;
+                    c = zk[r] - zp[r];
+                    if (r < 3) c -= dT * zp[3 + r];
+                    else if (r < 6) {
+                        const int a = r - 3;
+                        c -= dT * ((a == 2 ? GRAV_Z : 0.0) + tp[T_EXTF + a] + tp[T_EN] * d[SD_FC + a] + tp[T_EN + 1] * d[SD_FC + 3 + a]);
+                    } else if (r < 9) {
+                        const int a = r - 6, a1 = (a + 1) % 3, a2 = (a + 2) % 3;
+                        double tq = tp[T_EXTT + a];
+                        for (int cc = 0; cc < NC; ++cc) {
+                            double s = 0.0;
+                            for (int j = 0; j < NJ; ++j) {
+                                const double* rho = d + SD_RHO + 3 * (4 * cc + j);
+                                const double* fo = zp + NS + 6 + 12 * cc + 3 * j;
+                                s += rho[a1] * fo[a2] - rho[a2] * fo[a1];
+                            }
+                            tq += tp[T_EN + cc] * s;
+                        }
+                        c -= dT * tq;
+                    } else {
+                        const int cc = (r - 9) / 3;
+                        c -= tp[T_OMD + cc] * zp[NS + r - 9];
+                    }
+                }
+                c -= w.beq[k * ES + r];
+                w.ceq[k * ES + r] = c;
+                acc[1] += fabs(c);
+                // stage cost of s_k[r]
+                if (r < 2) { const double e = zk[r] - t[T_CREF + r]; acc[0] += cfg.w_com[r] * e * e; }
+                else if (r == 2) { const double e = zk[2] - t[T_CREF + 2]; acc[0] += t[T_OM2] * e * e; }
+                else if (r >= 6 && r < 9) { const double e = zk[r] - t[T_HREF + r - 6]; acc[0] += cfg.w_h * e * e; }
+                else if (r >= 9) { const double e = zk[r] - t[T_NOM + r - 9]; acc[0] += cfg.w_pos * e * e; }
+            } else if (k < N && r >= 16 && r < 16 + 38) {
+                const int l = r - 16, pr = k * PS + l;
+                const double g = path_dot(t, zk, zsrc + (k + 1) * ZS, l, 1);
+                w.gp[pr] = g;
+                const double sl = w.lo[pr], su = w.up[pr];
+                const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
+                if (hl || hu) {
+                    if (sl == su) acc[1] += fabs(g - sl);
+                    else {
+                        const double s = slsrc[pr];
+                        acc[1] += fabs(g - s);
+                        if (hl) acc[2] -= mu * log(s - sl);
+                        if (hu) acc[2] -= mu * log(su - s);
+                        if (hl && !hu) acc[2] += KAPPA_D * mu * (s - sl);
+                        if (hu && !hl) acc[2] += KAPPA_D * mu * (su - s);
+                    }
+                }
+            } else if (k < N && r >= 54 && r < 60) {
+                // force cost of (contact c, axis a): symmetry + rate of change
+                const int q = r - 54, c = q / 3, a = q - 3 * c;
+                const double en = t[T_EN + c];
+                const double* fc = zk + NS + 6 + 12 * c + a;
+                const double mean = en / NJ * (fc[0] + fc[3] + fc[6] + fc[9]);
+                for (int j = 0; j < NJ; ++j) {
+                    const double dd = fc[3 * j] - mean;
+                    acc[0] += cfg.w_sym * dd * dd;
+                    if (k + 1 < N) { const double dn = fc[3 * j + ZS] - fc[3 * j]; acc[0] += cfg.w_rate[a] * dn * dn; }
+                }
+            } else if (k < N && r >= 60 && r < 63) {
+                const int a = r - 60;
+                const double* d = w.sd + k * SD_STRIDE;
+                w.sd[k * SD_STRIDE + SD_FALL + a] = t[T_EN] * d[SD_FC + a] + t[T_EN + 1] * d[SD_FC + 3 + a];
+            }
+        }
+    CMPC_LANES_END_NOSYNC
+    cta.template sumv<3>(acc);
+    f = acc[0]; theta = acc[1]; phi = acc[0] + acc[2];
+}
+
+struct KktStats {
+    double dual, viol, pmax, pmin;    // max |grad_x L|, max violation, max / min of the products slack * multiplier
+    double sum_y, sum_z, nb, nrows;   // for the scaling factors s_d, s_c
+};
+// scaled optimality error E_mu (Waechter-Biegler eq. 5, 6) from the statistics of one KKT pass
+CMPC_HD double kkt_E(const KktStats& s, double mu, double* compl_out)
+{
+    const double cmp = s.nb > 0.0 ? fmax(fabs(s.pmax - mu), fabs(s.pmin - mu)) : 0.0;
+    const double sd = fmax(S_MAX, (s.sum_y + s.sum_z) / fmax(1.0, s.nrows + s.nb)) / S_MAX;
+    const double sc = fmax(S_MAX, s.sum_z / fmax(1.0, s.nb)) / S_MAX;
+    if (compl_out) *compl_out = cmp;
+    return fmax(s.dual / sd, fmax(s.viol, cmp / sc));
+}
+
+// one pass: gradient of f (stored), dual residual, violation, complementarity products, multiplier sums
+template <int NT, class Cta>
+CMPC_FN KktStats kkt_pass(Cta& cta, const Config& cfg, const WorkS& w)
+{
+    const int N = cfg.N;
+    // the values of the off-diagonal non-zeros of A at the iterate (needed by jty_entry and by the adjoint recursion)
+    CMPC_LANES
+        for (int it = lane; it < N * 16; it += NT) {
+            const int k = it >> 4, i = it & 15;
+            if (i < NS) {
+                double v2[2];
+                acol_vals(i, w.sd + k * SD_STRIDE, cfg.dT, v2);
+                w.aw[k * AWS + 2 * i] = v2[0]; w.aw[k * AWS + 2 * i + 1] = v2[1];
+            }
+        }
+    CMPC_LANES_END
+    double vmax[3] = {0.0, 0.0, -HUGE_VAL};   // dual, viol, pmax
+    double vmin[1] = {HUGE_VAL};              // pmin
+    double vsum[4] = {0.0, 0.0, 0.0, 0.0};    // |y|, z, bounds, rows
+    CMPC_LANES
+        for (int it = lane; it < (N + 1) * 128; it += NT) {
+            const int k = it >> 7, r = it & 127;
+            if (r < NS + NU) {
+                if (k == N && r >= NS) continue;
+                const double g = grad_entry(cfg, w, w.z, k, r);
+                w.gr[k * ZS + r] = g;
+                vmax[0] = fmax(vmax[0], fabs(g + jty_entry(cfg, w, w.lam, w.yp, k, r)));
+            } else if (r >= 48 && r < 48 + NS) {
+                const int e = k * ES + r - 48;
+                vmax[1] = fmax(vmax[1], fabs(w.ceq[e]));
+                vsum[0] += fabs(w.lam[e]);
+                vsum[3] += 1.0;
+            } else if (k < N && r >= 64 && r < 64 + 38) {
+                const int pr = k * PS + r - 64;
+                const double sl = w.lo[pr], su = w.up[pr];
+                const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
+                if (!hl && !hu) continue;
+                const double y = w.yp[pr], g = w.gp[pr];
+                vsum[0] += fabs(y);
+                vsum[3] += 1.0;
+                if (sl == su) { vmax[1] = fmax(vmax[1], fabs(g - sl)); continue; }
+                const double s = w.sl[pr];
+                vmax[1] = fmax(vmax[1], fabs(g - s));
+                double dsl = -y;
+                if (hl) { const double z = w.zl[pr], pd = (s - sl) * z; dsl -= z; vsum[1] += z; vsum[2] += 1.0; vmax[2] = fmax(vmax[2], pd); vmin[0] = fmin(vmin[0], pd); }
+                if (hu) { const double z = w.zu[pr], pd = (su - s) * z; dsl += z; vsum[1] += z; vsum[2] += 1.0; vmax[2] = fmax(vmax[2], pd); vmin[0] = fmin(vmin[0], pd); }
+                vmax[0] = fmax(vmax[0], fabs(dsl));
+            }
+        }
+    CMPC_LANES_END_NOSYNC
+    cta.template maxv<3>(vmax);
+    cta.template minv<1>(vmin);
+    cta.template sumv<4>(vsum);
+    KktStats s;
+    s.dual = vmax[0]; s.viol = vmax[1]; s.pmax = vmax[2]; s.pmin = vmin[0];
+    s.sum_y = vsum[0]; s.sum_z = vsum[1]; s.nb = vsum[2]; s.nrows = vsum[3];
+    return s;
+}
+
+// Sigma and the barrier gradient terms of the path rows, then the small blocks of the Riccati sweep for every knot
+template <int NT>
+CMPC_FN void barrier_pass(const Config& cfg, const WorkS& w, double mu, double dw, double dc)
+{
+    const int N = cfg.N;
+    CMPC_LANES
+        for (int it = lane; it < N * 64; it += NT) {
+            const int k = it >> 6, l = it & 63;
+            if (l >= 38) continue;
+            const int pr = k * PS + l;
+            const double sl = w.lo[pr], su = w.up[pr];
+            const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
+            double sg = 0.0, t = 0.0;
+            if (hl || hu) {
+                if (sl == su) { sg = 1.0 / dc; t = w.yp[pr] + (w.gp[pr] - sl) / dc; }
+                else {
+                    const double s = w.sl[pr];
+                    sg = dw;
+                    if (hl) { const double dd = s - sl; sg += w.zl[pr] / dd; t -= mu / dd; }
+                    if (hu) { const double dd = su - s; sg += w.zu[pr] / dd; t += mu / dd; }
+                    if (hl && !hu) t += KAPPA_D * mu;
+                    if (hu && !hl) t -= KAPPA_D * mu;
+                    t += sg * (w.gp[pr] - s);
+                }
+            }
+            w.sig[pr] = sg; w.tt[pr] = t;
+        }
+    CMPC_LANES_END
+    CMPC_LANES
+        for (int it = lane; it < (N + 1) * 128; it += NT) {
+            const int k = it >> 7, r = it & 127;
+            if (r >= 123) continue;
+            const double* t = w.tab + k * TS;
+            double val = 0.0;
+            if (r < 48) {  // friction barrier block of corner cj, packed entry e
+                if (k < N) {
+                    const int cj = r / 6, e = r - 6 * cj, c = cj >> 2;
+                    const int a = e < 3 ? 0 : (e < 5 ? 1 : 2), b = e < 3 ? e : (e < 5 ? e - 2 : 2);
+                    const double* ar = t + T_AR + 12 * c;
+                    const double* sg = w.sig + k * PS + 4 * cj;
+                    for (int q = 0; q < NF; ++q) val += sg[q] * ar[3 * q + a] * ar[3 * q + b];
+                }
+            } else if (r < 60) {  // step-box barrier block on pos_c of knot k (rows of knot k - 1)
+                if (k > 0) {
+                    const int t2 = r - 48, c = t2 / 6, e = t2 - 6 * c;
+                    const int a = e < 3 ? 0 : (e < 5 ? 1 : 2), b = e < 3 ? e : (e < 5 ? e - 2 : 2);
+                    const double* R = w.tab + (k - 1) * TS + T_R + 9 * c;
+                    const double* sg = w.sig + (k - 1) * PS + 32 + 3 * c;
+                    for (int q = 0; q < 3; ++q) val += sg[q] * R[3 * q + a] * R[3 * q + b];
+                }
+            } else if (r < 60 + NS) {
+                const int i = r - 60;
+                val = w.gr[k * ZS + i];
+                if (k > 0 && i >= 9) {
+                    const int c = (i - 9) / 3, a = (i - 9) % 3;
+                    const double* R = w.tab + (k - 1) * TS + T_R + 9 * c;
+                    const double* tb = w.tt + (k - 1) * PS + 32 + 3 * c;
+                    for (int q = 0; q < 3; ++q) val += R[3 * q + a] * tb[q];
+                }
+            } else if (r < 60 + NS + NU) {
+                if (k < N) {
+                    const int u = r - 60 - NS;
+                    val = w.gr[k * ZS + NS + u];
+                    if (u >= 6) {
+                        const int f = u - 6, c = f / 12, j = (f % 12) / 3, a = f % 3;
+                        const double* ar = t + T_AR + 12 * c + a;
+                        const double* tf = w.tt + k * PS + 16 * c + 4 * j;
+                        for (int q = 0; q < NF; ++q) val += ar[3 * q] * tf[q];
+                    }
+                }
+            } else if (r < 60 + NS + NU + NS) {
+                if (k < N) val = -w.ceq[(k + 1) * ES + r - 60 - NS - NU];
+            } else {
+                if (k < N) val = w.lam[(k + 1) * ES + 6 + r - 60 - NS - NU - NS];
+            }
+            w.small[(size_t)k * SMALL_STRIDE + r] = val;  // SmallBlk is laid out in item order
+        }
+    CMPC_LANES_END
+}
+
+// eliminated rows of the Newton system from dz (W-B eq. 13), then the multipliers of the equality rows by the adjoint
+// recursion  lambda+_k = A_k' lambda+_{k+1} - [grad f + W dz + sum_box a_i (y_i + dy_i)]_{s_k}  (exact for the given dz)
+template <int NT>
+CMPC_FN void recover_pass(const Config& cfg, const WorkS& w, double mu, double dw, double dc)
+{
+    const int N = cfg.N;
+    CMPC_LANES
+        for (int it = lane; it < N * 64; it += NT) {
+            const int k = it >> 6, l = it & 63;
+            if (l < 38) {
+                const int pr = k * PS + l;
+                const double sl = w.lo[pr], su = w.up[pr];
+                const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
+                double ds = 0.0, dzl = 0.0, dzu = 0.0, dy = 0.0;
+                if (hl || hu) {
+                    const double jd = path_dot(w.tab + k * TS, w.dz + k * ZS, w.dz + (k + 1) * ZS, l, 0);
+                    if (sl == su) dy = (jd + (w.gp[pr] - sl)) / dc;
+                    else {
+                        const double s = w.sl[pr];
+                        ds = jd + (w.gp[pr] - s);  // (g - s) first: jd can be below ulp(g)
+                        double rs = -w.yp[pr];
+                        if (hl) { const double dd = s - sl; rs -= mu / dd; dzl = mu / dd - w.zl[pr] - w.zl[pr] / dd * ds; }
+                        if (hu) { const double dd = su - s; rs += mu / dd; dzu = mu / dd - w.zu[pr] + w.zu[pr] / dd * ds; }
+                        if (hl && !hu) rs += KAPPA_D * mu;
+                        if (hu && !hl) rs -= KAPPA_D * mu;
+                        dy = w.sig[pr] * ds + rs;
+                    }
+                }
+                w.dsl[pr] = ds; w.dzl[pr] = dzl; w.dzu[pr] = dzu; w.dyp[pr] = dy;
+                w.ypn[pr] = w.yp[pr] + dy;
+            } else if (l >= 40 && l < 46) {  // step of the total force of contact c (for the bilinear hessian terms)
+                const int q = l - 40, c = q / 3, a = q - 3 * c;
+                const double* dc4 = w.dz + k * ZS + NS + 6 + 12 * c + a;
+                w.dfc[k * 8 + q] = dc4[0] + dc4[3] + dc4[6] + dc4[9];
+            }
+        }
+    CMPC_LANES_END
+    CMPC_LANES
+        for (int it = lane; it < (N + 1) * 16; it += NT) {
+            const int k = it >> 4, i = it & 15;
+            if (i >= NS) continue;
+            double v = w.gr[k * ZS + i] + hess_dz_entry(cfg, w, dw, k, i);
+            if (k > 0 && i >= 9) {
+                const int c = (i - 9) / 3, a = (i - 9) % 3;
+                const double* R = w.tab + (k - 1) * TS + T_R + 9 * c;
+                const double* yb = w.ypn + (k - 1) * PS + 32 + 3 * c;
+                v += R[a] * yb[0] + R[3 + a] * yb[1] + R[6 + a] * yb[2];
+            }
+            w.vco[k * ES + i] = v;
+        }
+    CMPC_LANES_END
+    // adjoint recursion on warp 0: lane i holds lambda+_k[i]; A' couples it with two other lanes
+    {
+        LaneVal lamp;
+        CMPC_WARP0
+            const double v = lane < NS ? -w.vco[N * ES + lane] : 0.0;
+            lamp.at(lane) = v;
+            if (lane < NS) { w.lamn[N * ES + lane] = v; w.dlam[N * ES + lane] = v - w.lam[N * ES + lane]; }
+        CMPC_WARP0_END
+#if defined(__CUDA_ARCH__)
+        if (threadIdx.x < 32)
+#endif
+        {
+            CMPC_ROLLED
+            for (int k = N - 1; k >= 0; --k) {
+                lamp.snapshot();
+                CMPC_WARP0
+                    int rr[2] = {0, 0};
+                    if (lane < NS) acol_rows(lane, rr);
+                    const double a0 = lamp.gather(lane, rr[0]), a1 = lamp.gather(lane, rr[1]);
+                    if (lane < NS) {
+                        const double v = -w.vco[k * ES + lane] + lamp.at(lane) + w.aw[k * AWS + 2 * lane] * a0 + w.aw[k * AWS + 2 * lane + 1] * a1;
+                        lamp.at(lane) = v;
+                        w.lamn[k * ES + lane] = v;
+                        w.dlam[k * ES + lane] = v - w.lam[k * ES + lane];
+                    }
+                CMPC_WARP0_END
+            }
+        }
+    }
+    team_sync<NT>();
+}
+
+struct StepStats { double rho, amax, az, dphi, bad; };
+// residual of the linearised stationarity (right hand side of the refinement) and, for the line search, the fraction to the
+// boundary (eq. 15) and the directional derivative of the barrier function
+template <int NT, class Cta>
+CMPC_FN StepStats step_pass(Cta& cta, const Config& cfg, const WorkS& w, double mu, double dw, double tau)
+{
+    const int N = cfg.N;
+    double vmax[2] = {0.0, 0.0};    // rho, non-finite flag
+    double vmin[2] = {1.0, 1.0};    // alpha_max (primal), alpha_z
+    double vsum[1] = {0.0};         // dphi
+    CMPC_LANES
+        for (int it = lane; it < (N + 1) * 128; it += NT) {
+            const int k = it >> 7, r = it & 127;
+            if (r < NS + NU) {
+                if (k == N && r >= NS) continue;
+                const double d = w.dz[k * ZS + r], g = w.gr[k * ZS + r];
+                double v = g + jty_entry(cfg, w, w.lamn, w.ypn, k, r) + hess_dz_entry(cfg, w, dw, k, r);
+                if (r >= NS && r < NS + 6 && w.tab[k * TS + T_VM + (r - NS) / 3] != 0.0) v = 0.0;  // variable held fixed
+                w.res[k * ZS + r] = v;
+                vmax[0] = fmax(vmax[0], fabs(v));
+                vsum[0] += g * d;
+                if (!(fabs(d) < HUGE_VAL)) vmax[1] = 1.0;
+            } else if (k < N && r >= 64 && r < 64 + 38) {
+                const int pr = k * PS + r - 64;
+                const double sl = w.lo[pr], su = w.up[pr];
+                const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
+                if ((!hl && !hu) || sl == su) continue;
+                const double s = w.sl[pr], ds = w.dsl[pr];
+                if (hl) {
+                    const double dd = s - sl, dz = w.dzl[pr];
+                    vsum[0] -= mu * ds / dd;
+                    if (ds < 0) vmin[0] = fmin(vmin[0], -tau * dd / ds);
+                    if (dz < 0) vmin[1] = fmin(vmin[1], -tau * w.zl[pr] / dz);
+                }
+                if (hu) {
+                    const double dd = su - s, dz = w.dzu[pr];
+                    vsum[0] += mu * ds / dd;
+                    if (ds > 0) vmin[0] = fmin(vmin[0], tau * dd / ds);
+                    if (dz < 0) vmin[1] = fmin(vmin[1], -tau * w.zu[pr] / dz);
+                }
+                if (hl && !hu) vsum[0] += KAPPA_D * mu * ds;
+                if (hu && !hl) vsum[0] -= KAPPA_D * mu * ds;
+            }
+        }
+    CMPC_LANES_END_NOSYNC
+    cta.template maxv<2>(vmax);
+    cta.template minv<2>(vmin);
+    cta.template sumv<1>(vsum);
+    StepStats s;
+    s.rho = vmax[0]; s.bad = vmax[1]; s.amax = vmin[0]; s.az = vmin[1]; s.dphi = vsum[0];
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------ the solver
+// x_io: in = initial guess, out = solution (CasADi order).  lam_io: multipliers of g (out; in when warm_duals).
+template <int NT, class Cta>
+CMPC_HD Result ipm_solve_team(Cta& cta, const Config& cfg, const Instance& in, WorkS w, WSmem& sm, double* x_io, double* lam_io,
+                              int warm_duals)
+{
+    const int N = cfg.N;
+    Result res;
+    res.status = 1; res.iters = 0; res.obj = 0; res.kkt = 0;
+    const bool warm = warm_duals && lam_io;
+
+    // ---- setup: table of constants, rows (classified, bounds relaxed by bound_relax_factor), iterate; validation
+    double bad[1] = {0.0};
+    CMPC_LANES
+        for (int it = lane; it < (N + 1) * 128; it += NT) {
+            const int k = it >> 7, r = it & 127;
+            if (r >= TS) continue;
+            const double* p = in.p;
+            const bool kn = k < N;
+            double v = 0.0;
+            if (r < 2) v = kn ? p[p_en(N, r, k)] : 0.0;
+            else if (r < 4) v = kn ? (1.0 - p[p_en(N, r - 2, k)]) * cfg.dT : 0.0;
+            else if (r < 6) v = kn ? (((1.0 - p[p_en(N, r - 4, k)]) * cfg.dT == 0.0) ? 1.0 : 0.0) : 0.0;
+            else if (r < 8) v = 0.0;
+            else if (r < 32) { const int q = r - 8, c = q / 12, rr = (q % 12) / 3, a = q % 3; v = kn ? fric_coef(cfg, p + p_rot(N, c, k), rr, a) : 0.0; }
+            else if (r < 50) { const int q = r - 32, c = q / 9; v = kn ? p[p_rot(N, c, k) + q % 9] : 0.0; }
+            else if (r < 74) {
+                const int q = r - 50, c = q / 12, j = (q % 12) / 3, a = q % 3;
+                if (kn) { const double* R = p + p_rot(N, c, k); const double* cr = cfg.corner[c][j]; v = R[a] * cr[0] + R[3 + a] * cr[1] + R[6 + a] * cr[2]; }
+            }
+            else if (r < 80) { const int q = r - 74; v = p[p_nom(N, q / 3, k) + q % 3]; }
+            else if (r < 86) { const int q = r - 80; v = kn ? p[p_nom(N, q / 3, k + 1) + q % 3] : 0.0; }
+            else if (r < 89) v = p[p_comref(N, k) + r - 86];
+            else if (r < 92) v = p[p_href(N, k) + r - 89];
+            else if (r < 95) v = kn ? p[p_extf(N, k) + r - 92] : 0.0;
+            else if (r < 98) v = kn ? p[p_extt(N, k) + r - 95] : 0.0;
+            else if (r == 98) { const double om = com_z_omega(cfg.w_com[2], k); v = om * om; }
+            w.tab[k * TS + r] = v;
+        }
+        for (int it = lane; it < (N + 1) * 64; it += NT) {
+            const int k = it >> 6, r = it & 63;
+            if (r < NS + NU) {
+                double v = 0.0;
+                if (!(k == N && r >= NS)) {
+                    v = x_io[r < NS ? x_of_s(N, k, r) : x_of_u(N, k, r - NS)];
+                    if (!(fabs(v) < HUGE_VAL)) bad[0] = 1.0;
+                }
+                w.z[k * ZS + r] = v;
+                w.dz[k * ZS + r] = 0.0;
+            } else if (r < ZS) {
+                w.z[k * ZS + r] = 0.0; w.dz[k * ZS + r] = 0.0; w.zt[k * ZS + r] = 0.0; w.gr[k * ZS + r] = 0.0; w.res[k * ZS + r] = 0.0;
+            } else if (r < ZS + ES) {
+                const int i = r - ZS, e = k * ES + i;
+                double b = 0.0, y = 0.0;
+                if (i < NS) {
+                    const int row = g_of_s(N, k, i);
+                    b = in.lbg[row];
+                    if (!(in.lbg[row] == in.ubg[row]) || !(fabs(b) < cfg.inf_bound)) bad[0] = 1.0;
+                    if (warm) y = lam_io[row];
+                }
+                w.beq[e] = b; w.lam[e] = y; w.dlam[e] = 0.0; w.ceq[e] = 0.0; w.lamn[e] = 0.0; w.vco[e] = 0.0;
+            }
+        }
+        for (int it = lane; it < N * 64; it += NT) {
+            const int k = it >> 6, l = it & 63;
+            if (l >= PS) continue;
+            const int pr = k * PS + l;
+            double lo = -HUGE_VAL, up = HUGE_VAL, y = 0.0;
+            if (l < 38) {
+                const int row = path_row(N, k, l);
+                const double lb = in.lbg[row], ub = in.ubg[row];
+                const bool hl = finite_lo(cfg, lb), hu = finite_up(cfg, ub);
+                if (!(lb == lb) || !(ub == ub) || (hl && hu && lb > ub)) bad[0] = 1.0;
+                if (hl && hu && lb == ub) { lo = lb; up = lb; }
+                else {
+                    if (hl) lo = lb - cfg.bound_relax * fmax(1.0, fabs(lb));
+                    if (hu) up = ub + cfg.bound_relax * fmax(1.0, fabs(ub));
+                }
+                if (warm && (hl || hu)) y = lam_io[row];
+            }
+            w.lo[pr] = lo; w.up[pr] = up; w.yp[pr] = y;
+            w.sl[pr] = 0.0; w.zl[pr] = 0.0; w.zu[pr] = 0.0; w.gp[pr] = 0.0; w.sig[pr] = 0.0; w.tt[pr] = 0.0;
+            w.dsl[pr] = 0.0; w.dzl[pr] = 0.0; w.dzu[pr] = 0.0; w.dyp[pr] = 0.0; w.ypn[pr] = 0.0; w.slt[pr] = 0.0;
+        }
+    CMPC_LANES_END_NOSYNC
+    cta.template maxv<1>(bad);
+    team_sync<NT>();
+    if (bad[0] != 0.0) { res.status = 4; return res; }
+
+    // ---- initial point: slacks pushed inside their bounds (bound_push / bound_frac), bound multipliers 1
+    double mu = cfg.mu_init, tau = fmax(TAU_MIN, 1.0 - mu);
+    const double mu_min = cfg.tol / (KAPPA_EPS + 1.0);
+    double f, theta0, phi0;
+    eval_point<NT>(cta, cfg, w, w.z, w.sl, mu, f, theta0, phi0);  // path row values (the slacks are not set yet)
+    CMPC_LANES
+        for (int it = lane; it < N * 64; it += NT) {
+            const int k = it >> 6, l = it & 63;
+            if (l >= 38) continue;
+            const int pr = k * PS + l;
+            const double sl = w.lo[pr], su = w.up[pr];
+            const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
+            if ((!hl && !hu) || sl == su) continue;
+            double s = w.gp[pr];
+            const double k1 = cfg.bound_push;
+            if (hl && hu) {
+                const double pl = fmin(k1 * fmax(1.0, fabs(sl)), k1 * (su - sl));
+                const double pu = fmin(k1 * fmax(1.0, fabs(su)), k1 * (su - sl));
+                s = fmin(fmax(s, sl + pl), su - pu);
+            } else if (hl) s = fmax(s, sl + k1 * fmax(1.0, fabs(sl)));
+            else s = fmin(s, su - k1 * fmax(1.0, fabs(su)));
+            w.sl[pr] = s;
+            double zl = hl ? 1.0 : 0.0, zu = hu ? 1.0 : 0.0;
+            if (warm) {
+                const double yv = w.yp[pr];
+                if (hl) zl = fmax(yv < 0 ? -yv : 0.0, cfg.mu_init / (s - sl));
+                if (hu) zu = fmax(yv > 0 ? yv : 0.0, cfg.mu_init / (su - s));
+            }
+            w.zl[pr] = zl; w.zu[pr] = zu;
+        }
+    CMPC_LANES_END
+    eval_point<NT>(cta, cfg, w, w.z, w.sl, mu, f, theta0, phi0);
+    const double theta_max = 1e4 * fmax(1.0, theta0), theta_min = 1e-4 * fmax(1.0, theta0);
+    double filt_t[MAX_FILTER], filt_p[MAX_FILTER];
+    int nfilt = 0;
+    double dw_last = 0.0;
+    double E0 = 0.0;
+    int it = 0, status = 1;
+    SweepIO io;
+    io.sd = w.sd; io.small = w.small; io.ric = w.ric; io.ceq = w.ceq; io.dz = w.dz; io.res = w.res;
+
+    for (it = 0; it <= cfg.max_iter; ++it) {
+        const KktStats ks = kkt_pass<NT>(cta, cfg, w);
+        double cmp0;
+        E0 = kkt_E(ks, 0.0, &cmp0);
+        if (E0 <= cfg.tol && ks.dual <= 1.0 && ks.viol <= 1e-4 && cmp0 <= 1e-4) { status = 0; break; }
+        if (it == cfg.max_iter) { status = 1; break; }
+        // barrier update (eq. 7), filter reset
+        bool mu_changed = false;
+        while (kkt_E(ks, mu, nullptr) <= KAPPA_EPS * mu && mu > mu_min) {
+            mu = fmax(mu_min, fmin(KAPPA_MU * mu, mu * sqrt(mu)));
+            tau = fmax(TAU_MIN, 1.0 - mu);
+            nfilt = 0;
+            mu_changed = true;
+        }
+        // ---- search direction with inertia correction (alg. IC): Cholesky failure inside the Riccati sweep <=> wrong inertia
+        const double dc = fmax(DC_BAR * sqrt(sqrt(mu)), DC_FLOOR);
+        double dw = 0.0;
+        int rc = 1, tries = 0;
+        for (;;) {
+            barrier_pass<NT>(cfg, w, mu, dw, dc);
+            rc = riccati_backward<NT>(cfg, io, sm, dw);
+            if (rc == 0) break;
+            if (dw == 0.0) dw = dw_last == 0.0 ? DW_FIRST : fmax(DW_MIN, KW_MINUS * dw_last);
+            else dw *= (dw_last == 0.0 ? KW_PLUS_FIRST : KW_PLUS);
+            if (dw > DW_MAX || ++tries > 60) break;
+        }
+        if (rc != 0) { status = 3; break; }
+        if (dw > 0.0) dw_last = dw;
+        riccati_forward<NT>(cfg, io, sm, false);
+        recover_pass<NT>(cfg, w, mu, dw, dc);
+        StepStats ss = step_pass<NT>(cta, cfg, w, mu, dw, tau);
+        // ---- iterative refinement on the stationarity residual of the Newton system (the eliminated rows hold exactly)
+        double rho_prev = HUGE_VAL;
+        for (int rf = 0; rf < MAX_REFINE; ++rf) {
+            if (!(ss.rho > REFINE_TOL) || ss.rho > 0.5 * rho_prev) break;
+            rho_prev = ss.rho;
+            refine_backward<NT>(cfg, io, sm);
+            riccati_forward<NT>(cfg, io, sm, true);
+            recover_pass<NT>(cfg, w, mu, dw, dc);
+            ss = step_pass<NT>(cta, cfg, w, mu, dw, tau);
+        }
+        if (ss.bad != 0.0) { status = 3; break; }
+        const double amax = ss.amax, az = ss.az, dphi = ss.dphi;
+        // ---- filter line search (alg. A)
+        double theta, phi;
+        if (mu_changed || it == 0) {
+            double ff;
+            eval_point<NT>(cta, cfg, w, w.z, w.sl, mu, ff, theta, phi);  // barrier function of the current point for the new mu
+        } else { theta = theta0; phi = phi0; }
+        double amin;
+        if (dphi < 0) {
+            amin = fmin(GAMMA_THETA, GAMMA_PHI * theta / (-dphi));
+            if (theta <= theta_min) amin = fmin(amin, DELTA_SW * pow(theta, S_THETA) / pow(-dphi, S_PHI));
+        } else amin = GAMMA_THETA;
+        amin *= GAMMA_ALPHA;
+        double alpha = amax, ft = f, th_t = theta, ph_t = phi;
+        int accepted = 0, armijo = 0;
+        while (alpha >= amin || alpha == amax) {
+            CMPC_LANES
+                for (int i = lane; i < (N + 1) * ZS; i += NT) w.zt[i] = w.z[i] + alpha * w.dz[i];
+                for (int i = lane; i < N * PS; i += NT) w.slt[i] = w.sl[i] + alpha * w.dsl[i];
+            CMPC_LANES_END
+            eval_point<NT>(cta, cfg, w, w.zt, w.slt, mu, ft, th_t, ph_t);
+            bool ok = (fabs(ph_t) < HUGE_VAL) && (fabs(th_t) < HUGE_VAL) && th_t <= theta_max;
+            for (int q = 0; ok && q < nfilt; ++q)
+                if (th_t >= filt_t[q] && ph_t >= filt_p[q]) ok = false;
+            if (ok) {
+                const bool sw = dphi < 0 && theta <= theta_min && alpha * pow(-dphi, S_PHI) > DELTA_SW * pow(theta, S_THETA);
+                const double slack = 10.0 * 2.2e-16 * fabs(phi);
+                if (sw) {
+                    if (ph_t - phi - slack <= ETA_PHI * alpha * dphi) { accepted = 1; armijo = 1; }
+                } else if (th_t <= (1.0 - GAMMA_THETA) * theta || ph_t - slack <= phi - GAMMA_PHI * theta) {
+                    accepted = 1; armijo = 0;
+                }
+            }
+            if (accepted) break;
+            alpha *= 0.5;
+            if (alpha < 1e-16) break;
+        }
+        if (!accepted) { status = 2; break; }  // IPOPT would start its restoration phase here (not restated)
+        if (!armijo && nfilt < MAX_FILTER) {
+            filt_t[nfilt] = (1.0 - GAMMA_THETA) * theta;
+            filt_p[nfilt] = phi - GAMMA_PHI * theta;
+            nfilt++;
+        }
+        // ---- accept the trial point (ceq, gp, sd already hold its values): swap the buffers, update the multipliers
+        { double* tmp = w.z; w.z = w.zt; w.zt = tmp; tmp = w.sl; w.sl = w.slt; w.slt = tmp; }
+        f = ft; theta0 = th_t; phi0 = ph_t;
+        CMPC_LANES
+            for (int i = lane; i < N * PS; i += NT) {
+                const double sl = w.lo[i], su = w.up[i];
+                const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
+                w.yp[i] += alpha * w.dyp[i];
+                if ((!hl && !hu) || sl == su) continue;
+                const double s = w.sl[i];
+                if (hl) {
+                    const double z = w.zl[i] + az * w.dzl[i], dd = s - sl;
+                    w.zl[i] = fmax(fmin(z, KAPPA_SIGMA * mu / dd), mu / (KAPPA_SIGMA * dd));
+                }
+                if (hu) {
+                    const double z = w.zu[i] + az * w.dzu[i], dd = su - s;
+                    w.zu[i] = fmax(fmin(z, KAPPA_SIGMA * mu / dd), mu / (KAPPA_SIGMA * dd));
+                }
+            }
+            for (int i = lane; i < (N + 1) * ES; i += NT) w.lam[i] += alpha * w.dlam[i];
+        CMPC_LANES_END
+    }
+    // ---- solution back to the CasADi order
+    CMPC_LANES
+        for (int i2 = lane; i2 < (N + 1) * 64; i2 += NT) {
+            const int k = i2 >> 6, r = i2 & 63;
+            if (r < NS + NU) {
+                if (k == N && r >= NS) continue;
+                x_io[r < NS ? x_of_s(N, k, r) : x_of_u(N, k, r - NS)] = w.z[k * ZS + r];
+            } else if (lam_io && r >= ZS && r < ZS + NS) {
+                lam_io[g_of_s(N, k, r - ZS)] = w.lam[k * ES + r - ZS];
+            }
+        }
+        if (lam_io)
+            for (int i2 = lane; i2 < N * 64; i2 += NT) {
+                const int k = i2 >> 6, l = i2 & 63;
+                if (l < 38) lam_io[path_row(N, k, l)] = w.yp[k * PS + l];
+            }
+    CMPC_LANES_END
+    res.status = status; res.iters = it; res.obj = f; res.kkt = E0;
+    return res;
+}
+
+}  // namespace cmpc

@@ -18,7 +18,7 @@
 
 #include "../../include/cmpc_b200.h"
 #include "cmpc_sparse.cuh"
-#include "cmpc_warp.cuh"
+#include "cmpc_ipm.cuh"
 
 namespace cmpc {
 
@@ -109,9 +109,8 @@ cmpc_solve_team_kernel(const __grid_constant__ Config cfg, int batch, const doub
     if constexpr (NT != 32) cta.red = sm.red;
     const int N = cfg.N, n = dim_x(N), np = dim_p(N), m = dim_g(N);
     double* base = work + (size_t)blockIdx.x * work_stride;
-    Work w;
-    work_carve(base, N, w);
-    LinTeam<NT> lin{sm, WorkW{base + work_doubles(N), base + work_doubles(N) + (N + 1) * SMALL_STRIDE}};
+    WorkS w;
+    works_carve(base, N, w);
     for (;;) {
         if (threadIdx.x == 0) s_inst = (int)atomicAdd(counter, 1u);
         team_sync<NT>();
@@ -119,7 +118,7 @@ cmpc_solve_team_kernel(const __grid_constant__ Config cfg, int batch, const doub
         team_sync<NT>();
         if (inst >= batch) break;
         Instance in{p + (size_t)inst * np, lbg + (size_t)inst * m, ubg + (size_t)inst * m};
-        Result r = ipm_solve(cta, cfg, in, w, lin, x + (size_t)inst * n, lam ? lam + (size_t)inst * m : nullptr, warm_duals);
+        Result r = ipm_solve_team<NT>(cta, cfg, in, w, sm, x + (size_t)inst * n, lam ? lam + (size_t)inst * m : nullptr, warm_duals);
         if (threadIdx.x == 0) {
             if (obj) obj[inst] = r.obj;
             if (status) status[inst] = r.status;
@@ -457,7 +456,7 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
     if (e != cudaSuccess || occ < 1) { h->last_cuda = (int)e; delete h; return CMPC_E_CUDA; }
     h->ctas_per_sm = (u->ctas_per_sm > 0 && u->ctas_per_sm < occ) ? u->ctas_per_sm : occ;
     h->grid = h->sm_count * h->ctas_per_sm;  // persistent grid: a multiple of the SM count
-    h->work_stride = ((size_t)(work_doubles(c.N) + workw_doubles(c.N)) + 15) & ~(size_t)15;
+    h->work_stride = ((size_t)works_doubles(c.N) + 15) & ~(size_t)15;
     Csc jc, hc;
     build_csc(c.N, false, jc);
     build_csc(c.N, true, hc);

@@ -7,7 +7,7 @@
 #include <cstring>
 #include <vector>
 
-#include "../../paper_romualdi_2022_icra_centroidal-mpc-walking_b200/csrc/cmpc_warp.cuh"
+#include "../../paper_romualdi_2022_icra_centroidal-mpc-walking_b200/csrc/cmpc_ipm.cuh"
 
 namespace {
 struct HostCta {
@@ -43,14 +43,12 @@ static int solve_team(const cmpc::Config* cfg, const double* p, const double* lb
                       int warm_duals, int* iters, double* obj, double* kkt)
 {
     HostCta cta;
-    std::vector<double> buf(cmpc::work_doubles(cfg->N) + cmpc::workw_doubles(cfg->N), 0.0);
-    cmpc::Work w;
-    cmpc::work_carve(buf.data(), cfg->N, w);
+    std::vector<double> buf(cmpc::works_doubles(cfg->N), 0.0);
+    cmpc::WorkS w;
+    cmpc::works_carve(buf.data(), cfg->N, w);
     static cmpc::WSmem sm;
     cmpc::Instance in{p, lbg, ubg};
-    cmpc::LinTeam<NT> lin{sm, cmpc::WorkW{buf.data() + cmpc::work_doubles(cfg->N),
-                                          buf.data() + cmpc::work_doubles(cfg->N) + (cfg->N + 1) * cmpc::SMALL_STRIDE}};
-    cmpc::Result r = cmpc::ipm_solve(cta, *cfg, in, w, lin, x, lam, warm_duals);
+    cmpc::Result r = cmpc::ipm_solve_team<NT>(cta, *cfg, in, w, sm, x, lam, warm_duals);
     *iters = r.iters; *obj = r.obj; *kkt = r.kkt;
     return r.status;
 }
