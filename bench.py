@@ -38,15 +38,15 @@ FLOP_CANON_PER_ITER_KNOT = 422275.0
 FP64_PEAK_FALLBACK_TFLOPS = 37.0  # vendor figure (HGX B200 296 TF / 8); used only if the live DFMA probe fails
 
 
-def workload(name: str, pkg, wl, seed: int):
+def workload(name: str, pkg, wl, seed: int, batch: int = 0):
     if name == "icub3_b1024":
         cfg = pkg.icub3_config()
-        w = wl.walk_batch(N=15, dT=0.1, B=1024, seed=seed, state_noise=1.0, step_adjust=False)
+        w = wl.walk_batch(N=15, dT=0.1, B=batch or 1024, seed=seed, state_noise=1.0, step_adjust=False)
         ocfg = dict(N=15, w_com=(1.0, 1.0, 200.0), w_pos=200.0, w_sym=0.0,
                     corners=[[(0.08, 0.03, 0), (0.08, -0.03, 0), (-0.08, -0.03, 0), (-0.08, 0.03, 0)]] * 2)
     elif name == "ergocub_b65536":
         cfg = pkg.ergocub_config()
-        w = wl.walk_batch(N=12, dT=0.1, B=65536, seed=seed, state_noise=2.0, yaw_range=0.3, step_adjust=True)
+        w = wl.walk_batch(N=12, dT=0.1, B=batch or 65536, seed=seed, state_noise=2.0, yaw_range=0.3, step_adjust=True)
         ocfg = dict(N=12, w_pos=2000.0)
     else:
         raise SystemExit(f"unknown workload {name}")
@@ -115,7 +115,7 @@ def run_reference(args):
         @staticmethod
         def ergocub_config():
             return None
-    _, w, ocfg = workload(args.workload, _P, pkg_wl, seed=0)
+    _, w, ocfg = workload(args.workload, _P, pkg_wl, seed=0, batch=getattr(args, "batch", 0))
     cores = os.cpu_count() or 1
     sample = min(w["p"].shape[0], max(8, 2 * cores))
     times = []
@@ -145,7 +145,8 @@ def main():
     ap.add_argument("--workload", default="icub3_b1024")
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--team", type=int, default=0, help="threads per instance (32/64/128), 0 = library default")
+    ap.add_argument("--team", type=int, default=0, help="threads per instance (32/64/96/128), 0 = library default")
+    ap.add_argument("--batch", type=int, default=0, help="instances per GPU (0 = the workload's own size)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -165,7 +166,7 @@ def main():
 
     pkg = importlib.import_module(PKG)
     wl = importlib.import_module(PKG + ".workloads")
-    cfg, w, ocfg = workload(args.workload, pkg, wl, seed=rank)   # every rank its own shard of instances
+    cfg, w, ocfg = workload(args.workload, pkg, wl, seed=rank, batch=args.batch)   # every rank its own shard of instances
     cfg.device = local
     cfg.ipopt_tolerance = args.tol
     cfg.threads_per_instance = args.team

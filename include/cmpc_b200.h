@@ -65,7 +65,7 @@ typedef struct cmpc_config {
     double bound_push;                      /* IPOPT bound_push = bound_frac, default 0.01                          */
     double infinity;                        /* |bound| >= infinity means no bound, default 1e19                     */
     int device;                             /* CUDA device ordinal                                                  */
-    int threads_per_instance;               /* team size: 32, 64 or 128 threads per instance, 0 = default (128)     */
+    int threads_per_instance;               /* team size: 32, 64, 96 or 128 threads per instance, 0 = default (96)  */
     int ctas_per_sm;                        /* resident CTAs per SM used to size the persistent grid, 0 = occupancy */
 } cmpc_config;
 
@@ -124,6 +124,9 @@ int cmpc_rollout_plant(cmpc_handle h, int batch, const double* d_x, const double
 /* measured FP64 FMA throughput of the handle's device [TFLOP/s]: 8 independent DFMA chains per thread, no memory traffic.
  * The denominator of the solver kernel's FP64 roofline (MEASURED_PEAKS.json has no FP64 figure). */
 int cmpc_measure_fp64_peak(cmpc_handle h, double* tflops);
+
+/* debugging aid: accumulated clock64() cycles of thread 0 per solve phase (all zeros unless built with -DCMPC_PROFILE) */
+int cmpc_debug_profile(long long* out16);
 
 /* number of kernels this handle has launched so far, and the last CUDA error code seen by any call */
 long long cmpc_launch_count(cmpc_handle h);

@@ -55,6 +55,26 @@ CMPC_HD void works_carve(double* base, int N, WorkS& w)
     w.ric = c;
 }
 
+struct KktStats {
+    double dual, viol, pmax, pmin;    // max |grad_x L|, max violation, max / min of the products slack * multiplier
+    double sum_y, sum_z, nb, nrows;   // for the scaling factors s_d, s_c
+};
+struct StepStats { double rho, amax, az, dphi, bad; };
+struct EvalStats { double f, theta, phi; };
+
+// shared memory of one team: the Riccati block first (P at offset 0: 16-byte aligned async copies), then everything the
+// interior-point loop would otherwise keep on the thread stacks.  Local memory is poison here: the shared-memory carve-out
+// leaves almost no L1, so every stack access is an L2 round trip (ncu: as many local loads as global loads, 83 % missing L1).
+struct ISmem {
+    WSmem sw;
+    WorkS w;                 // array pointers of the instance's scratch block
+    SweepIO io;
+    KktStats ks;
+    StepStats ss;
+    EvalStats es;
+    double filt_t[MAX_FILTER], filt_p[MAX_FILTER];
+};
+
 // CasADi row of path row l of knot k
 CMPC_HD int path_row(int N, int k, int l)
 {
@@ -82,7 +102,7 @@ CMPC_HD double path_dot(const double* tab, const double* zk, const double* zk1, 
 }
 
 // gradient of the objective in variable v (0..44) of knot k at the point zsrc
-CMPC_HD double grad_entry(const Config& cfg, const WorkS& w, const double* zsrc, int k, int v)
+CMPC_FN double grad_entry(const Config& cfg, const WorkS& w, const double* zsrc, int k, int v)
 {
     const int N = cfg.N;
     const double* t = w.tab + k * TS;
@@ -107,7 +127,7 @@ CMPC_HD double grad_entry(const Config& cfg, const WorkS& w, const double* zsrc,
 }
 
 // (J' y)[variable v of knot k] for multipliers lam (equality rows, stage major) and yp (path rows); needs sd / aw at the iterate
-CMPC_HD double jty_entry(const Config& cfg, const WorkS& w, const double* lam, const double* yp, int k, int v)
+CMPC_FN double jty_entry(const Config& cfg, const WorkS& w, const double* lam, const double* yp, int k, int v)
 {
     const int N = cfg.N;
     if (v < NS) {
@@ -141,7 +161,7 @@ CMPC_HD double jty_entry(const Config& cfg, const WorkS& w, const double* lam, c
 }
 
 // (W dz)[variable v of knot k]: hessian of the lagrangian (nlp_hess_l, tmp.c:58926) + delta_w I, times the step
-CMPC_HD double hess_dz_entry(const Config& cfg, const WorkS& w, double dw, int k, int v)
+CMPC_FN double hess_dz_entry(const Config& cfg, const WorkS& w, double dw, int k, int v)
 {
     const int N = cfg.N;
     const double* t = w.tab + k * TS;
@@ -179,9 +199,9 @@ CMPC_HD double hess_dz_entry(const Config& cfg, const WorkS& w, double dw, int k
 // ------------------------------------------------------------------------------------------------ evaluation of a point
 // stage data, equality residuals, path row values, objective, theta (l1 infeasibility) and the barrier function at (zsrc, slsrc)
 template <int NT, class Cta>
-CMPC_FN void eval_point(Cta& cta, const Config& cfg, const WorkS& w, const double* zsrc, const double* slsrc, double mu, double& f,
-                        double& theta, double& phi)
+CMPC_FN void eval_point(Cta& cta, const Config& cfg, ISmem& sm, const double* zsrc, const double* slsrc, double mu)
 {
+    const WorkS& w = sm.w;
     const int N = cfg.N;
     const double dT = cfg.dT;
     CMPC_LANES
@@ -283,14 +303,12 @@ CMPC_FN void eval_point(Cta& cta, const Config& cfg, const WorkS& w, const doubl
             }
         }
     CMPC_LANES_END_NOSYNC
-    cta.template sumv<3>(acc);
-    f = acc[0]; theta = acc[1]; phi = acc[0] + acc[2];
+    cta.template reduce3<0, 0, 3>(acc, acc, acc);
+    CMPC_LANES
+        if (lane == 0) { sm.es.f = acc[0]; sm.es.theta = acc[1]; sm.es.phi = acc[0] + acc[2]; }
+    CMPC_LANES_END
 }
 
-struct KktStats {
-    double dual, viol, pmax, pmin;    // max |grad_x L|, max violation, max / min of the products slack * multiplier
-    double sum_y, sum_z, nb, nrows;   // for the scaling factors s_d, s_c
-};
 // scaled optimality error E_mu (Waechter-Biegler eq. 5, 6) from the statistics of one KKT pass
 CMPC_HD double kkt_E(const KktStats& s, double mu, double* compl_out)
 {
@@ -303,8 +321,9 @@ CMPC_HD double kkt_E(const KktStats& s, double mu, double* compl_out)
 
 // one pass: gradient of f (stored), dual residual, violation, complementarity products, multiplier sums
 template <int NT, class Cta>
-CMPC_FN KktStats kkt_pass(Cta& cta, const Config& cfg, const WorkS& w)
+CMPC_FN void kkt_pass(Cta& cta, const Config& cfg, ISmem& sm)
 {
+    const WorkS& w = sm.w;
     const int N = cfg.N;
     // the values of the off-diagonal non-zeros of A at the iterate (needed by jty_entry and by the adjoint recursion)
     CMPC_LANES
@@ -351,13 +370,14 @@ CMPC_FN KktStats kkt_pass(Cta& cta, const Config& cfg, const WorkS& w)
             }
         }
     CMPC_LANES_END_NOSYNC
-    cta.template maxv<3>(vmax);
-    cta.template minv<1>(vmin);
-    cta.template sumv<4>(vsum);
-    KktStats s;
-    s.dual = vmax[0]; s.viol = vmax[1]; s.pmax = vmax[2]; s.pmin = vmin[0];
-    s.sum_y = vsum[0]; s.sum_z = vsum[1]; s.nb = vsum[2]; s.nrows = vsum[3];
-    return s;
+    cta.template reduce3<3, 1, 4>(vmax, vmin, vsum);
+    CMPC_LANES
+        if (lane == 0) {
+            KktStats& s = sm.ks;
+            s.dual = vmax[0]; s.viol = vmax[1]; s.pmax = vmax[2]; s.pmin = vmin[0];
+            s.sum_y = vsum[0]; s.sum_z = vsum[1]; s.nb = vsum[2]; s.nrows = vsum[3];
+        }
+    CMPC_LANES_END
 }
 
 // Sigma and the barrier gradient terms of the path rows, then the small blocks of the Riccati sweep for every knot
@@ -523,12 +543,12 @@ CMPC_FN void recover_pass(const Config& cfg, const WorkS& w, double mu, double d
     team_sync<NT>();
 }
 
-struct StepStats { double rho, amax, az, dphi, bad; };
 // residual of the linearised stationarity (right hand side of the refinement) and, for the line search, the fraction to the
 // boundary (eq. 15) and the directional derivative of the barrier function
 template <int NT, class Cta>
-CMPC_FN StepStats step_pass(Cta& cta, const Config& cfg, const WorkS& w, double mu, double dw, double tau)
+CMPC_FN void step_pass(Cta& cta, const Config& cfg, ISmem& sm, double mu, double dw, double tau)
 {
+    const WorkS& w = sm.w;
     const int N = cfg.N;
     double vmax[2] = {0.0, 0.0};    // rho, non-finite flag
     double vmin[2] = {1.0, 1.0};    // alpha_max (primal), alpha_z
@@ -568,21 +588,31 @@ CMPC_FN StepStats step_pass(Cta& cta, const Config& cfg, const WorkS& w, double 
             }
         }
     CMPC_LANES_END_NOSYNC
-    cta.template maxv<2>(vmax);
-    cta.template minv<2>(vmin);
-    cta.template sumv<1>(vsum);
-    StepStats s;
-    s.rho = vmax[0]; s.bad = vmax[1]; s.amax = vmin[0]; s.az = vmin[1]; s.dphi = vsum[0];
-    return s;
+    cta.template reduce3<2, 2, 1>(vmax, vmin, vsum);
+    CMPC_LANES
+        if (lane == 0) {
+            StepStats& s = sm.ss;
+            s.rho = vmax[0]; s.bad = vmax[1]; s.amax = vmin[0]; s.az = vmin[1]; s.dphi = vsum[0];
+        }
+    CMPC_LANES_END
 }
 
 // ------------------------------------------------------------------------------------------------ the solver
 // x_io: in = initial guess, out = solution (CasADi order).  lam_io: multipliers of g (out; in when warm_duals).
 template <int NT, class Cta>
-CMPC_HD Result ipm_solve_team(Cta& cta, const Config& cfg, const Instance& in, WorkS w, WSmem& sm, double* x_io, double* lam_io,
-                              int warm_duals)
+CMPC_HD Result ipm_solve_team(Cta& cta, const Config& cfg, const Instance& in, double* scratch, ISmem& ism,
+                              const unsigned short* cmap, double* x_io, double* lam_io, int warm_duals)
 {
     const int N = cfg.N;
+    WSmem& sm = ism.sw;
+    WorkS& w = ism.w;
+    SweepIO& io = ism.io;
+    CMPC_LANES
+        if (lane == 0) {
+            works_carve(scratch, N, w);
+            io.sd = w.sd; io.small = w.small; io.ric = w.ric; io.ceq = w.ceq; io.dz = w.dz; io.res = w.res; io.cmap = cmap;
+        }
+    CMPC_LANES_END
     Result res;
     res.status = 1; res.iters = 0; res.obj = 0; res.kkt = 0;
     const bool warm = warm_duals && lam_io;
@@ -669,7 +699,7 @@ CMPC_HD Result ipm_solve_team(Cta& cta, const Config& cfg, const Instance& in, W
     double mu = cfg.mu_init, tau = fmax(TAU_MIN, 1.0 - mu);
     const double mu_min = cfg.tol / (KAPPA_EPS + 1.0);
     double f, theta0, phi0;
-    eval_point<NT>(cta, cfg, w, w.z, w.sl, mu, f, theta0, phi0);  // path row values (the slacks are not set yet)
+    eval_point<NT>(cta, cfg, ism, w.z, w.sl, mu);  // path row values (the slacks are not set yet)
     CMPC_LANES
         for (int it = lane; it < N * 64; it += NT) {
             const int k = it >> 6, l = it & 63;
@@ -696,18 +726,22 @@ CMPC_HD Result ipm_solve_team(Cta& cta, const Config& cfg, const Instance& in, W
             w.zl[pr] = zl; w.zu[pr] = zu;
         }
     CMPC_LANES_END
-    eval_point<NT>(cta, cfg, w, w.z, w.sl, mu, f, theta0, phi0);
+    eval_point<NT>(cta, cfg, ism, w.z, w.sl, mu);
+    f = ism.es.f; theta0 = ism.es.theta; phi0 = ism.es.phi;
     const double theta_max = 1e4 * fmax(1.0, theta0), theta_min = 1e-4 * fmax(1.0, theta0);
-    double filt_t[MAX_FILTER], filt_p[MAX_FILTER];
+    double* filt_t = ism.filt_t;
+    double* filt_p = ism.filt_p;
     int nfilt = 0;
     double dw_last = 0.0;
     double E0 = 0.0;
     int it = 0, status = 1;
-    SweepIO io;
-    io.sd = w.sd; io.small = w.small; io.ric = w.ric; io.ceq = w.ceq; io.dz = w.dz; io.res = w.res;
 
+    CMPC_TIC
+    CMPC_TOC(0)
     for (it = 0; it <= cfg.max_iter; ++it) {
-        const KktStats ks = kkt_pass<NT>(cta, cfg, w);
+        kkt_pass<NT>(cta, cfg, ism);
+        CMPC_TOC(1)
+        const KktStats ks = ism.ks;
         double cmp0;
         E0 = kkt_E(ks, 0.0, &cmp0);
         if (E0 <= cfg.tol && ks.dual <= 1.0 && ks.viol <= 1e-4 && cmp0 <= 1e-4) { status = 0; break; }
@@ -726,7 +760,9 @@ CMPC_HD Result ipm_solve_team(Cta& cta, const Config& cfg, const Instance& in, W
         int rc = 1, tries = 0;
         for (;;) {
             barrier_pass<NT>(cfg, w, mu, dw, dc);
+            CMPC_TOC(2)
             rc = riccati_backward<NT>(cfg, io, sm, dw);
+            CMPC_TOC(3)
             if (rc == 0) break;
             if (dw == 0.0) dw = dw_last == 0.0 ? DW_FIRST : fmax(DW_MIN, KW_MINUS * dw_last);
             else dw *= (dw_last == 0.0 ? KW_PLUS_FIRST : KW_PLUS);
@@ -735,8 +771,12 @@ CMPC_HD Result ipm_solve_team(Cta& cta, const Config& cfg, const Instance& in, W
         if (rc != 0) { status = 3; break; }
         if (dw > 0.0) dw_last = dw;
         riccati_forward<NT>(cfg, io, sm, false);
+        CMPC_TOC(4)
         recover_pass<NT>(cfg, w, mu, dw, dc);
-        StepStats ss = step_pass<NT>(cta, cfg, w, mu, dw, tau);
+        CMPC_TOC(5)
+        step_pass<NT>(cta, cfg, ism, mu, dw, tau);
+        StepStats ss = ism.ss;
+        CMPC_TOC(6)
         // ---- iterative refinement on the stationarity residual of the Newton system (the eliminated rows hold exactly)
         double rho_prev = HUGE_VAL;
         for (int rf = 0; rf < MAX_REFINE; ++rf) {
@@ -745,15 +785,17 @@ CMPC_HD Result ipm_solve_team(Cta& cta, const Config& cfg, const Instance& in, W
             refine_backward<NT>(cfg, io, sm);
             riccati_forward<NT>(cfg, io, sm, true);
             recover_pass<NT>(cfg, w, mu, dw, dc);
-            ss = step_pass<NT>(cta, cfg, w, mu, dw, tau);
+            step_pass<NT>(cta, cfg, ism, mu, dw, tau);
+            ss = ism.ss;
         }
+        CMPC_TOC(7)
         if (ss.bad != 0.0) { status = 3; break; }
         const double amax = ss.amax, az = ss.az, dphi = ss.dphi;
         // ---- filter line search (alg. A)
         double theta, phi;
         if (mu_changed || it == 0) {
-            double ff;
-            eval_point<NT>(cta, cfg, w, w.z, w.sl, mu, ff, theta, phi);  // barrier function of the current point for the new mu
+            eval_point<NT>(cta, cfg, ism, w.z, w.sl, mu);  // barrier function of the current point for the new mu
+            theta = ism.es.theta; phi = ism.es.phi;
         } else { theta = theta0; phi = phi0; }
         double amin;
         if (dphi < 0) {
@@ -768,7 +810,8 @@ CMPC_HD Result ipm_solve_team(Cta& cta, const Config& cfg, const Instance& in, W
                 for (int i = lane; i < (N + 1) * ZS; i += NT) w.zt[i] = w.z[i] + alpha * w.dz[i];
                 for (int i = lane; i < N * PS; i += NT) w.slt[i] = w.sl[i] + alpha * w.dsl[i];
             CMPC_LANES_END
-            eval_point<NT>(cta, cfg, w, w.zt, w.slt, mu, ft, th_t, ph_t);
+            eval_point<NT>(cta, cfg, ism, w.zt, w.slt, mu);
+            ft = ism.es.f; th_t = ism.es.theta; ph_t = ism.es.phi;
             bool ok = (fabs(ph_t) < HUGE_VAL) && (fabs(th_t) < HUGE_VAL) && th_t <= theta_max;
             for (int q = 0; ok && q < nfilt; ++q)
                 if (th_t >= filt_t[q] && ph_t >= filt_p[q]) ok = false;
@@ -785,14 +828,19 @@ CMPC_HD Result ipm_solve_team(Cta& cta, const Config& cfg, const Instance& in, W
             alpha *= 0.5;
             if (alpha < 1e-16) break;
         }
+        CMPC_TOC(8)
         if (!accepted) { status = 2; break; }  // IPOPT would start its restoration phase here (not restated)
         if (!armijo && nfilt < MAX_FILTER) {
-            filt_t[nfilt] = (1.0 - GAMMA_THETA) * theta;
-            filt_p[nfilt] = phi - GAMMA_PHI * theta;
+            CMPC_LANES
+                if (lane == 0) { filt_t[nfilt] = (1.0 - GAMMA_THETA) * theta; filt_p[nfilt] = phi - GAMMA_PHI * theta; }
+            CMPC_LANES_END_NOSYNC
             nfilt++;
         }
         // ---- accept the trial point (ceq, gp, sd already hold its values): swap the buffers, update the multipliers
-        { double* tmp = w.z; w.z = w.zt; w.zt = tmp; tmp = w.sl; w.sl = w.slt; w.slt = tmp; }
+        team_sync<NT>();
+        CMPC_LANES
+            if (lane == 0) { double* tmp = w.z; w.z = w.zt; w.zt = tmp; tmp = w.sl; w.sl = w.slt; w.slt = tmp; }
+        CMPC_LANES_END
         f = ft; theta0 = th_t; phi0 = ph_t;
         CMPC_LANES
             for (int i = lane; i < N * PS; i += NT) {
@@ -812,6 +860,7 @@ CMPC_HD Result ipm_solve_team(Cta& cta, const Config& cfg, const Instance& in, W
             }
             for (int i = lane; i < (N + 1) * ES; i += NT) w.lam[i] += alpha * w.dlam[i];
         CMPC_LANES_END
+        CMPC_TOC(9)
     }
     // ---- solution back to the CasADi order
     CMPC_LANES

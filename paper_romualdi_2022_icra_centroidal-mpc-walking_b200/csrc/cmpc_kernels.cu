@@ -55,6 +55,41 @@ struct DevCta {
     template <int K> __device__ __forceinline__ void minv(double* v) { allreduce<K>(v, [](double a, double b) { return fmin(a, b); }); }
     __device__ __forceinline__ double sum(double x) { sumv<1>(&x); return x; }
     __device__ __forceinline__ double max(double x) { maxv<1>(&x); return x; }
+    // KM maxima, KN minima and KS sums in ONE exchange through shared memory (KM + KN + KS <= 8, at most 8 warps)
+    template <int KM, int KN, int KS>
+    __device__ __forceinline__ void reduce3(double* vmax, double* vmin, double* vsum)
+    {
+        constexpr int K = KM + KN + KS;
+        const int nw = nt >> 5;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int op = k < KM ? 0 : (k < KM + KN ? 1 : 2);
+            double* src = k < KM ? vmax + k : (k < KM + KN ? vmin + (k - KM) : vsum + (k - KM - KN));
+            const double x = warp_reduce_op(*src, op);
+            if (lane == 0) red[warp * K + k] = x;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int op = k < KM ? 0 : (k < KM + KN ? 1 : 2);
+            double* dst = k < KM ? vmax + k : (k < KM + KN ? vmin + (k - KM) : vsum + (k - KM - KN));
+            double x = red[k];
+            for (int w2 = 1; w2 < nw; ++w2) x = combine_op(x, red[w2 * K + k], op);
+            *dst = x;
+        }
+        __syncthreads();
+    }
+    static __device__ __forceinline__ double combine_op(double x, double y, int op)
+    {
+        return op == 0 ? (x > y ? x : y) : (op == 1 ? (x < y ? x : y) : x + y);
+    }
+    // butterfly over the warp with a run-time operation: one copy of the code for every statistic of every pass
+    static __device__ __noinline__ double warp_reduce_op(double x, int op)
+    {
+#pragma unroll 1
+        for (int off = 16; off > 0; off >>= 1) x = combine_op(x, __shfl_xor_sync(0xffffffffu, x, off), op);
+        return x;
+    }
 };
 
 __device__ __forceinline__ DevCta make_cta(double* red)
@@ -86,6 +121,13 @@ struct DevWarp {
     template <int K> __device__ __forceinline__ void minv(double* v) { allreduce<K>(v, [](double a, double b) { return fmin(a, b); }); }
     __device__ __forceinline__ double sum(double x) { sumv<1>(&x); return x; }
     __device__ __forceinline__ double max(double x) { maxv<1>(&x); return x; }
+    template <int KM, int KN, int KS>
+    __device__ __forceinline__ void reduce3(double* vmax, double* vmin, double* vsum)
+    {
+        if (KM > 0) maxv<KM == 0 ? 1 : KM>(vmax);
+        if (KN > 0) minv<KN == 0 ? 1 : KN>(vmin);
+        if (KS > 0) sumv<KS == 0 ? 1 : KS>(vsum);
+    }
 };
 
 // ------------------------------------------------------------------------------------------------ kernels
@@ -99,18 +141,17 @@ template <int NT, int CTAS>
 __global__ void __launch_bounds__(NT, CTAS)
 cmpc_solve_team_kernel(const __grid_constant__ Config cfg, int batch, const double* __restrict__ p,
                        const double* __restrict__ lbg, const double* __restrict__ ubg, double* x, double* lam, double* obj,
-                       int* status, int* iters, int warm_duals, double* work, size_t work_stride, unsigned int* counter)
+                       int* status, int* iters, int warm_duals, double* work, size_t work_stride, unsigned int* counter,
+                       const unsigned short* __restrict__ cmap)
 {
-    extern __shared__ double smem_raw[];
-    WSmem& sm = *reinterpret_cast<WSmem*>(smem_raw);
+    extern __shared__ __align__(16) double smem_raw[];
+    ISmem& sm = *reinterpret_cast<ISmem*>(smem_raw);
     __shared__ int s_inst;
     typename TeamCta<NT>::type cta;
     cta.tid = threadIdx.x; cta.nt = NT; cta.warp = threadIdx.x >> 5; cta.lane = threadIdx.x & 31; cta.wsize = 32;
-    if constexpr (NT != 32) cta.red = sm.red;
+    if constexpr (NT != 32) cta.red = sm.sw.red;
     const int N = cfg.N, n = dim_x(N), np = dim_p(N), m = dim_g(N);
     double* base = work + (size_t)blockIdx.x * work_stride;
-    WorkS w;
-    works_carve(base, N, w);
     for (;;) {
         if (threadIdx.x == 0) s_inst = (int)atomicAdd(counter, 1u);
         team_sync<NT>();
@@ -118,7 +159,7 @@ cmpc_solve_team_kernel(const __grid_constant__ Config cfg, int batch, const doub
         team_sync<NT>();
         if (inst >= batch) break;
         Instance in{p + (size_t)inst * np, lbg + (size_t)inst * m, ubg + (size_t)inst * m};
-        Result r = ipm_solve_team<NT>(cta, cfg, in, w, sm, x + (size_t)inst * n, lam ? lam + (size_t)inst * m : nullptr, warm_duals);
+        Result r = ipm_solve_team<NT>(cta, cfg, in, base, sm, cmap, x + (size_t)inst * n, lam ? lam + (size_t)inst * m : nullptr, warm_duals);
         if (threadIdx.x == 0) {
             if (obj) obj[inst] = r.obj;
             if (status) status[inst] = r.status;
@@ -324,7 +365,7 @@ static void build_csc(int N, bool hess, Csc& out)
 using namespace cmpc;
 
 #ifndef CMPC_DEFAULT_TEAM
-#define CMPC_DEFAULT_TEAM 128
+#define CMPC_DEFAULT_TEAM 96
 #endif
 #ifndef CMPC_CTAS_PER_SM
 #define CMPC_CTAS_PER_SM 7
@@ -345,6 +386,7 @@ struct cmpc_handle_s {
     double* d_work = nullptr;
     unsigned int* d_counter = nullptr;
     int *d_jslot = nullptr, *d_hslot = nullptr;
+    unsigned short* d_cmap = nullptr;
     double* d_gscratch = nullptr;
     // staging buffers of cmpc_solve_host
     int host_cap = 0;
@@ -448,7 +490,7 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
     // threads_per_instance: team size, 32 / 64 / 128 (0 = default)
     h->threads = u->threads_per_instance == 0 ? CMPC_DEFAULT_TEAM : u->threads_per_instance;
     if (h->threads != 32 && h->threads != 64 && h->threads != 96 && h->threads != 128) { delete h; return CMPC_E_INVALID; }
-    h->smem = (int)sizeof(WSmem);
+    h->smem = (int)sizeof(ISmem);
     const void* kfn = team_kernel(h->threads);
     int occ = 0;
     e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
@@ -464,11 +506,17 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
         cudaMalloc(&h->d_counter, sizeof(unsigned int)) != cudaSuccess ||
         cudaMalloc(&h->d_jslot, sizeof(int) * jc.slot.size()) != cudaSuccess ||
         cudaMalloc(&h->d_hslot, sizeof(int) * hc.slot.size()) != cudaSuccess ||
+        cudaMalloc(&h->d_cmap, sizeof(unsigned short) * CF_DINV) != cudaSuccess ||
         cudaMalloc(&h->d_gscratch, sizeof(double) * dim_g(c.N) * h->sm_count * 4) != cudaSuccess) {
         cmpc_destroy(h);
         return CMPC_E_ALLOC;
     }
     cudaMemset(h->d_work, 0, sizeof(double) * h->work_stride * h->grid);
+    {
+        std::vector<unsigned short> cm(CF_DINV);
+        build_cmap(cm.data());
+        cudaMemcpy(h->d_cmap, cm.data(), sizeof(unsigned short) * CF_DINV, cudaMemcpyHostToDevice);
+    }
     cudaMemcpy(h->d_jslot, jc.slot.data(), sizeof(int) * jc.slot.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(h->d_hslot, hc.slot.data(), sizeof(int) * hc.slot.size(), cudaMemcpyHostToDevice);
     *out = h;
@@ -479,7 +527,7 @@ int cmpc_destroy(cmpc_handle h)
 {
     if (!h) return CMPC_E_INVALID;
     cudaSetDevice(h->device);
-    cudaFree(h->d_work); cudaFree(h->d_counter); cudaFree(h->d_jslot); cudaFree(h->d_hslot); cudaFree(h->d_gscratch);
+    cudaFree(h->d_work); cudaFree(h->d_counter); cudaFree(h->d_jslot); cudaFree(h->d_hslot); cudaFree(h->d_gscratch); cudaFree(h->d_cmap);
     cudaFree(h->d_p); cudaFree(h->d_lbg); cudaFree(h->d_ubg); cudaFree(h->d_x); cudaFree(h->d_lam); cudaFree(h->d_obj);
     cudaFree(h->d_status); cudaFree(h->d_iters);
     delete h;
@@ -499,7 +547,7 @@ int cmpc_solve_batched(cmpc_handle h, int batch, const double* d_p, const double
 #define CMPC_LAUNCH_TEAM(NT)                                                                                                  \
     cmpc_solve_team_kernel<NT, CMPC_CTAS_PER_SM><<<grid, NT, h->smem, st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj, \
                                                                             d_status, d_iters, warm_duals, h->d_work,        \
-                                                                            h->work_stride, h->d_counter)
+                                                                            h->work_stride, h->d_counter, h->d_cmap)
     if (h->threads == 32) CMPC_LAUNCH_TEAM(32);
     else if (h->threads == 64) CMPC_LAUNCH_TEAM(64);
     else if (h->threads == 96) CMPC_LAUNCH_TEAM(96);
@@ -649,6 +697,19 @@ int cmpc_measure_fp64_peak(cmpc_handle h, double* tflops)
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     *tflops = best;
+    return CMPC_OK;
+}
+
+// cycle counters of the solve phases (zeros unless the library was built with -DCMPC_PROFILE); resets them
+int cmpc_debug_profile(long long* out16)
+{
+    if (!out16) return CMPC_E_INVALID;
+    memset(out16, 0, 16 * sizeof(long long));
+#if defined(CMPC_PROFILE)
+    long long z[16] = {0};
+    cudaMemcpyFromSymbol(out16, cmpc::g_prof, sizeof z);
+    cudaMemcpyToSymbol(cmpc::g_prof, z, sizeof z);
+#endif
     return CMPC_OK;
 }
 

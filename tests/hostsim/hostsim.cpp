@@ -19,6 +19,7 @@ struct HostCta {
     template <int K> void sumv(double*) {}
     template <int K> void maxv(double*) {}
     template <int K> void minv(double*) {}
+    template <int KM, int KN, int KS> void reduce3(double*, double*, double*) {}
 };
 }  // namespace
 
@@ -44,11 +45,11 @@ static int solve_team(const cmpc::Config* cfg, const double* p, const double* lb
 {
     HostCta cta;
     std::vector<double> buf(cmpc::works_doubles(cfg->N), 0.0);
-    cmpc::WorkS w;
-    cmpc::works_carve(buf.data(), cfg->N, w);
-    static cmpc::WSmem sm;
+    static cmpc::ISmem sm;
     cmpc::Instance in{p, lbg, ubg};
-    cmpc::Result r = cmpc::ipm_solve_team<NT>(cta, *cfg, in, w, sm, x, lam, warm_duals);
+    static unsigned short cmap[cmpc::CF_DINV];
+    cmpc::build_cmap(cmap);
+    cmpc::Result r = cmpc::ipm_solve_team<NT>(cta, *cfg, in, buf.data(), sm, cmap, x, lam, warm_duals);
     *iters = r.iters; *obj = r.obj; *kkt = r.kkt;
     return r.status;
 }
