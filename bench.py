@@ -117,7 +117,7 @@ def run_reference(args):
             return None
     _, w, ocfg = workload(args.workload, _P, pkg_wl, seed=0, batch=getattr(args, "batch", 0))
     cores = os.cpu_count() or 1
-    sample = min(w["p"].shape[0], max(8, 2 * cores))
+    sample = min(w["p"].shape[0], max(64, 16 * cores))
     times = []
     for s in range(args.warmup + args.steps):
         rate, dt, ok, its = cpu_oracle_rate(ocfg, w, sample, cores, 1e-8)
@@ -166,6 +166,7 @@ def main():
 
     pkg = importlib.import_module(PKG)
     wl = importlib.import_module(PKG + ".workloads")
+    sharding = importlib.import_module(PKG + ".sharding")
     cfg, w, ocfg = workload(args.workload, pkg, wl, seed=rank, batch=args.batch)   # every rank its own shard of instances
     cfg.device = local
     cfg.ipopt_tolerance = args.tol
@@ -178,13 +179,12 @@ def main():
     d_x = d_x0.clone()
     d_lam = torch.zeros(B, m, dtype=torch.float64, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2
-    gather = [torch.empty(B, 3, dtype=torch.float64, device=dev) for _ in range(world)] if world > 1 else None
 
     def step():
         d_x.copy_(d_x0)
         obj, status, iters, _ = solver.solve(d_p, d_lbg, d_ubg, d_x, d_lam)
-        if world > 1:  # the only exchange of the sharded job: gather per-instance results
-            dist.all_gather(gather, torch.stack([obj, status.double(), iters.double()], dim=1))
+        # the only exchange of the sharded job: gather per-instance results
+        sharding.gather_results(sharding.pack_results(obj, status, iters), world)
         return obj, status, iters
 
     for _ in range(args.warmup):
@@ -207,8 +207,7 @@ def main():
         kev[s][0].record()
         obj, status, iters, _ = solver.solve(d_p, d_lbg, d_ubg, d_x, d_lam)
         kev[s][1].record()
-        if world > 1:
-            dist.all_gather(gather, torch.stack([obj, status.double(), iters.double()], dim=1))
+        sharding.gather_results(sharding.pack_results(obj, status, iters), world)
         ev[s][1].record()
     torch.cuda.synchronize()
     if world > 1:
@@ -226,6 +225,22 @@ def main():
     status_h, iters_h = status.cpu().numpy(), iters.cpu().numpy()
     conv = int((status_h == 0).sum())
     total_iters = int(iters_h.sum())
+
+    # ---- single-solve latency (the second half of BASELINE.json's metric): batch of ONE instance, device resident, p50
+    lat = []
+    if rank == 0:
+        x1 = d_x0[:1].clone()
+        for j in range(15):
+            x1.copy_(d_x0[:1])
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            solver.solve(d_p[:1], d_lbg[:1], d_ubg[:1], x1, d_lam[:1])
+            b.record()
+            torch.cuda.synchronize()
+            if j >= 3:
+                lat.append(a.elapsed_time(b))
+    if world > 1:
+        dist.barrier()
 
     # ---- end to end through the host-pointer C-ABI call with pinned host buffers
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
@@ -292,6 +307,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": k_e2e, "api": "cmpc_solve_host (pinned host buffers)"},
             "gpu_launches": int(launches),
+            "latency": {"p50_single_solve_ms": float(np.median(lat)) if lat else None, "samples": len(lat),
+                        "iterations": int(iters_h[0]), "note": "batch of one instance, device resident, cold start"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "traffic": None, "peak_source": peak_src, "kernel": "cmpc_solve_team_kernel",
                          "kernel_ms_per_launch": 1e3 * kernel_s, "flop_executed_per_launch": flop_exec,
@@ -303,7 +320,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            sample = min(B, max(8, 2 * cores))
+            sample = min(B, max(64, 32 * cores))   # about 10-30 core-seconds of CPU work
             rate, dt, ok, its = cpu_oracle_rate(ocfg, w, sample, cores, args.tol)
             line["cpu_baseline"] = {"value": rate, "unit": "solves/s", "cores": cores, "kind": "port",
                                     "sample": f"first {sample} instances of the workload, {dt:.1f} s, {ok}/{sample} "

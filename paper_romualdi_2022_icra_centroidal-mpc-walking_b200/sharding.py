@@ -1,0 +1,35 @@
+"""Multi-GPU plumbing of the batched solve: instances are independent, so ranks own contiguous index ranges and the only
+exchange is one all_gather of the per-instance results (objective, status, iterations) at the end of a batch
+(SURVEY.md 8(e)).  torch.distributed is the transport (NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(total: int, rank: int, world: int) -> tuple[int, int]:
+    """contiguous range [lo, hi) of instance indices owned by `rank`; sizes differ by at most one"""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pack_results(obj: torch.Tensor, status: torch.Tensor, iters: torch.Tensor) -> torch.Tensor:
+    """(B, 3) float64: objective, status, iterations of every instance of the local shard"""
+    return torch.stack([obj.double(), status.double(), iters.double()], dim=1)
+
+
+def gather_results(local: torch.Tensor, world: int, sizes: list[int] | None = None) -> torch.Tensor:
+    """all_gather of the packed local results; `sizes` = rows per rank when the shards are uneven (padded exchange)"""
+    if world == 1:
+        return local
+    n = max(sizes) if sizes else local.shape[0]
+    buf = local
+    if local.shape[0] < n:
+        buf = torch.zeros(n, local.shape[1], dtype=local.dtype, device=local.device)
+        buf[: local.shape[0]] = local
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf)
+    if sizes:
+        out = [o[:s] for o, s in zip(out, sizes)]
+    return torch.cat(out, dim=0)
