@@ -45,8 +45,10 @@ def walk_batch(N=12, dT=0.1, B=1, seed=0, phase=None, yaw_range=0.0, state_noise
     P = 2 * (ds + ss)
     if phase is None:
         ph = rng.integers(0, P, size=B)
-    else:
+    elif np.ndim(phase) == 0:
         ph = np.full(B, int(phase))
+    else:
+        ph = np.asarray(phase, dtype=np.int64).reshape(B)
     ell = ph[:, None] + np.arange(N + 1)[None, :]               # global knot index (B, N+1)
     q, cyc = ell % P, ell // P
 
@@ -139,7 +141,10 @@ def walk_batch(N=12, dT=0.1, B=1, seed=0, phase=None, yaw_range=0.0, state_noise
         x0[:, L.x_com(k):L.x_com(k) + 3] = comref[:, k]
     if push is not None:
         p[:, L.p_extf(0):L.p_extf(0) + 3] = np.asarray(push, dtype=np.float64).reshape(B, 3)
-    return dict(p=p, lbg=lbg, ubg=ubg, x0=x0, N=N, dT=dT, phase=ph)
+    # knots whose nominal position refers to the contact the foot stands on at knot 0 (incl. the lift-off knot), and the
+    # stance flag at knot 0: what a closed loop needs to replace planned by actual footsteps (rollout.py)
+    same = np.stack([(step[c] == step[c][:, :1]) & ~swing[c][:, :1] for c in range(NC)])
+    return dict(p=p, lbg=lbg, ubg=ubg, x0=x0, N=N, dT=dT, phase=ph, same_contact=same, stance0=~swing[:, :, 0], comref=comref)
 
 
 def scenario_s0(dcom0=(0.0, 0.0, 0.0)):
