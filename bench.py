@@ -146,6 +146,8 @@ def main():
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--team", type=int, default=0, help="threads per instance (32/64/96/128), 0 = library default")
+    ap.add_argument("--identical", action="store_true", help="experiment: every instance is a copy of instance 0")
+    ap.add_argument("--ctas", type=int, default=0, help="resident teams per SM (0 = occupancy)")
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (0 = the workload's own size)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -168,9 +170,13 @@ def main():
     wl = importlib.import_module(PKG + ".workloads")
     sharding = importlib.import_module(PKG + ".sharding")
     cfg, w, ocfg = workload(args.workload, pkg, wl, seed=rank, batch=args.batch)   # every rank its own shard of instances
+    if args.identical:
+        for key in ("p", "lbg", "ubg", "x0"):
+            w[key] = np.repeat(w[key][:1], w[key].shape[0], axis=0)
     cfg.device = local
     cfg.ipopt_tolerance = args.tol
     cfg.threads_per_instance = args.team
+    cfg.ctas_per_sm = args.ctas
     solver = pkg.BatchedCentroidalMPC(cfg)
     B, N = w["p"].shape[0], cfg.horizon
     n, m, npar = solver.L.n, solver.L.m, solver.L.np

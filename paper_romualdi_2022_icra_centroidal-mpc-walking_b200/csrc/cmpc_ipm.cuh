@@ -19,6 +19,14 @@
 
 namespace cmpc {
 
+#if defined(__CUDA_ARCH__)
+#define CMPC_UNROLL2 _Pragma("unroll 2")
+#define CMPC_UNROLL4 _Pragma("unroll 4")
+#else
+#define CMPC_UNROLL2
+#define CMPC_UNROLL4
+#endif
+
 constexpr int PS = 40;  // stride of a knot in the path-row arrays: friction 0..31 (16 c + 4 j + r) | step box 32..37 (32 + 3 c + q) | pad
 // per-knot table of constants
 constexpr int TS = 100;
@@ -386,26 +394,28 @@ CMPC_FN void barrier_pass(const Config& cfg, const WorkS& w, double mu, double d
 {
     const int N = cfg.N;
     CMPC_LANES
-        for (int it = lane; it < N * 64; it += NT) {
-            const int k = it >> 6, l = it & 63;
-            if (l >= 38) continue;
-            const int pr = k * PS + l;
-            const double sl = w.lo[pr], su = w.up[pr];
-            const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
-            double sg = 0.0, t = 0.0;
-            if (hl || hu) {
-                if (sl == su) { sg = 1.0 / dc; t = w.yp[pr] + (w.gp[pr] - sl) / dc; }
-                else {
-                    const double s = w.sl[pr];
-                    sg = dw;
-                    if (hl) { const double dd = s - sl; sg += w.zl[pr] / dd; t -= mu / dd; }
-                    if (hu) { const double dd = su - s; sg += w.zu[pr] / dd; t += mu / dd; }
-                    if (hl && !hu) t += KAPPA_D * mu;
-                    if (hu && !hl) t -= KAPPA_D * mu;
-                    t += sg * (w.gp[pr] - s);
+        {
+            const double* __restrict__ lo = w.lo; const double* __restrict__ up = w.up; const double* __restrict__ ypp = w.yp;
+            const double* __restrict__ gpp = w.gp; const double* __restrict__ slp = w.sl; const double* __restrict__ zlp = w.zl;
+            const double* __restrict__ zup = w.zu; double* __restrict__ sigp = w.sig; double* __restrict__ ttp = w.tt;
+            CMPC_UNROLL2
+            for (int pr = lane; pr < N * PS; pr += NT) {  // the two pad rows of every knot have no bounds: sig = tt = 0
+                const double sl = lo[pr], su = up[pr], y = ypp[pr], g = gpp[pr], s = slp[pr], zl = zlp[pr], zu = zup[pr];
+                const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
+                double sg = 0.0, t = 0.0;
+                if (hl || hu) {
+                    if (sl == su) { sg = 1.0 / dc; t = y + (g - sl) / dc; }
+                    else {
+                        sg = dw;
+                        if (hl) { const double dd = s - sl; sg += zl / dd; t -= mu / dd; }
+                        if (hu) { const double dd = su - s; sg += zu / dd; t += mu / dd; }
+                        if (hl && !hu) t += KAPPA_D * mu;
+                        if (hu && !hl) t -= KAPPA_D * mu;
+                        t += sg * (g - s);
+                    }
                 }
+                sigp[pr] = sg; ttp[pr] = t;
             }
-            w.sig[pr] = sg; w.tt[pr] = t;
         }
     CMPC_LANES_END
     CMPC_LANES
@@ -807,8 +817,14 @@ CMPC_HD Result ipm_solve_team(Cta& cta, const Config& cfg, const Instance& in, d
         int accepted = 0, armijo = 0;
         while (alpha >= amin || alpha == amax) {
             CMPC_LANES
-                for (int i = lane; i < (N + 1) * ZS; i += NT) w.zt[i] = w.z[i] + alpha * w.dz[i];
-                for (int i = lane; i < N * PS; i += NT) w.slt[i] = w.sl[i] + alpha * w.dsl[i];
+                {
+                    double* __restrict__ zt = w.zt; const double* __restrict__ z = w.z; const double* __restrict__ dz = w.dz;
+                    double* __restrict__ slt = w.slt; const double* __restrict__ sl = w.sl; const double* __restrict__ dsl = w.dsl;
+                    CMPC_UNROLL4
+                    for (int i = lane; i < (N + 1) * ZS; i += NT) zt[i] = z[i] + alpha * dz[i];
+                    CMPC_UNROLL4
+                    for (int i = lane; i < N * PS; i += NT) slt[i] = sl[i] + alpha * dsl[i];
+                }
             CMPC_LANES_END
             eval_point<NT>(cta, cfg, ism, w.zt, w.slt, mu);
             ft = ism.es.f; th_t = ism.es.theta; ph_t = ism.es.phi;
@@ -843,19 +859,22 @@ CMPC_HD Result ipm_solve_team(Cta& cta, const Config& cfg, const Instance& in, d
         CMPC_LANES_END
         f = ft; theta0 = th_t; phi0 = ph_t;
         CMPC_LANES
-            for (int i = lane; i < N * PS; i += NT) {
-                const double sl = w.lo[i], su = w.up[i];
-                const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
-                w.yp[i] += alpha * w.dyp[i];
-                if ((!hl && !hu) || sl == su) continue;
-                const double s = w.sl[i];
-                if (hl) {
-                    const double z = w.zl[i] + az * w.dzl[i], dd = s - sl;
-                    w.zl[i] = fmax(fmin(z, KAPPA_SIGMA * mu / dd), mu / (KAPPA_SIGMA * dd));
-                }
-                if (hu) {
-                    const double z = w.zu[i] + az * w.dzu[i], dd = su - s;
-                    w.zu[i] = fmax(fmin(z, KAPPA_SIGMA * mu / dd), mu / (KAPPA_SIGMA * dd));
+            {
+                // every load of an item is issued before anything depends on it: one memory round trip per item
+                double* __restrict__ yp = w.yp; double* __restrict__ zlp = w.zl; double* __restrict__ zup = w.zu;
+                const double* __restrict__ lo = w.lo; const double* __restrict__ up = w.up; const double* __restrict__ slp = w.sl;
+                const double* __restrict__ dyp = w.dyp; const double* __restrict__ dzl = w.dzl; const double* __restrict__ dzu = w.dzu;
+                CMPC_UNROLL2
+                for (int i = lane; i < N * PS; i += NT) {
+                    const double sl = lo[i], su = up[i], s = slp[i], y = yp[i], dy = dyp[i], zl0 = zlp[i], dl = dzl[i], zu0 = zup[i], du = dzu[i];
+                    const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
+                    const bool ineq = (hl || hu) && !(sl == su);
+                    yp[i] = y + alpha * dy;
+                    const double ddl = s - sl, ddu = su - s;
+                    const double zl1 = fmax(fmin(zl0 + az * dl, KAPPA_SIGMA * mu / ddl), mu / (KAPPA_SIGMA * ddl));
+                    const double zu1 = fmax(fmin(zu0 + az * du, KAPPA_SIGMA * mu / ddu), mu / (KAPPA_SIGMA * ddu));
+                    if (ineq && hl) zlp[i] = zl1;
+                    if (ineq && hu) zup[i] = zu1;
                 }
             }
             for (int i = lane; i < (N + 1) * ES; i += NT) w.lam[i] += alpha * w.dlam[i];

@@ -497,6 +497,11 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, h->threads, h->smem);
     if (e != cudaSuccess || occ < 1) { h->last_cuda = (int)e; delete h; return CMPC_E_CUDA; }
     h->ctas_per_sm = (u->ctas_per_sm > 0 && u->ctas_per_sm < occ) ? u->ctas_per_sm : occ;
+    if (h->ctas_per_sm < occ) {  // fewer resident teams than fit: give the rest of the shared-memory carve-out back to L1
+        int pct = (int)((100.0 * h->ctas_per_sm * (h->smem + 1024)) / (228.0 * 1024.0)) + 1;
+        if (pct > 100) pct = 100;
+        cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
     h->grid = h->sm_count * h->ctas_per_sm;  // persistent grid: a multiple of the SM count
     h->work_stride = ((size_t)works_doubles(c.N) + 15) & ~(size_t)15;
     Csc jc, hc;
