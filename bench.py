@@ -33,7 +33,7 @@ PKG = "paper_romualdi_2022_icra_centroidal-mpc-walking_b200"
 
 # FP64 flop executed per interior-point iteration and knot by cmpc_solve_kernel (measured with ncu, see
 # profiles/ and DESIGN.md "flop accounting"), and the canonical dense figure of SURVEY.md 8(d)
-FLOP_EXEC_PER_ITER_KNOT = 1.68e5
+FLOP_EXEC_PER_ITER_KNOT = 1.22e5
 FLOP_CANON_PER_ITER_KNOT = 422275.0
 FP64_PEAK_FALLBACK_TFLOPS = 37.0  # vendor figure (HGX B200 296 TF / 8); used only if the live DFMA probe fails
 
