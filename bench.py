@@ -35,6 +35,7 @@ PKG = "paper_romualdi_2022_icra_centroidal-mpc-walking_b200"
 # profiles/ and DESIGN.md "flop accounting"), and the canonical dense figure of SURVEY.md 8(d)
 FLOP_EXEC_PER_ITER_KNOT = 1.22e5
 FLOP_CANON_PER_ITER_KNOT = 422275.0
+DRAM_TRAFFIC_PER_LAUNCH = 1.127e10   # bytes, ncu (icub3_b1024, team 96)
 FP64_PEAK_FALLBACK_TFLOPS = 37.0  # vendor figure (HGX B200 296 TF / 8); used only if the live DFMA probe fails
 
 
@@ -54,23 +55,28 @@ def workload(name: str, pkg, wl, seed: int, batch: int = 0):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe): one nvidia-smi process in loop
+    mode (-lms 50), its lines are collected while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
 
     def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.strip().split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+        finally:
+            if self.proc is not None:
+                self.proc.kill()
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
@@ -201,6 +207,8 @@ def main():
         dist.barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    time.sleep(0.15)   # nvidia-smi start-up: the first sample must fall inside the timed region
+    sampler.rows.clear()
     launches0 = solver.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -316,7 +324,10 @@ def main():
             "latency": {"p50_single_solve_ms": float(np.median(lat)) if lat else None, "samples": len(lat),
                         "iterations": int(iters_h[0]), "note": "batch of one instance, device resident, cold start"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "traffic": None, "peak_source": peak_src, "kernel": "cmpc_solve_team_kernel",
+                         "traffic": DRAM_TRAFFIC_PER_LAUNCH if (args.workload == "icub3_b1024" and B == 1024) else None,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu capture prof_t96c "
+                                         "(profiles/r1_notes.md): the solver's scratch (iterate vectors + Riccati factors of 1036 "
+                                         "resident teams) does not fit the 126 MB L2", "peak_source": peak_src, "kernel": "cmpc_solve_team_kernel",
                          "kernel_ms_per_launch": 1e3 * kernel_s, "flop_executed_per_launch": flop_exec,
                          "flop_canonical_dense_per_launch": flop_canon,
                          "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / kernel_s / 1e9,
