@@ -11,7 +11,7 @@ HOSTLIB = os.path.join(HERE, "libcmpc_host.so")
 SOURCES = [os.path.join(HERE, "csrc", "cmpc_kernels.cu")]
 DEPS = [os.path.join(HERE, "csrc", f) for f in ("cmpc_kernels.cu", "cmpc_core.cuh", "cmpc_warp.cuh", "cmpc_ipm.cuh", "cmpc_layout.cuh", "cmpc_sparse.cuh")]
 DEPS.append(os.path.join(os.path.dirname(HERE), "include", "cmpc_b200.h"))
-HOST_SOURCES = [os.path.join(HERE, "host", f) for f in ("CentroidalMPC.cpp", "IniParametersHandler.cpp", "Contacts.cpp", "capi.cpp")]
+HOST_SOURCES = [os.path.join(HERE, "host", f) for f in ("CentroidalMPC.cpp", "IniParametersHandler.cpp", "Contacts.cpp", "BlockUtilities.cpp", "capi.cpp")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
               "--extended-lambda", "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550"]
@@ -39,7 +39,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         subprocess.run(cmd, check=True)
     host_src = [s for s in HOST_SOURCES if os.path.exists(s)]
     hdir = os.path.join(HERE, "host", "BipedalLocomotion")
-    hdeps = host_src + ([os.path.join(hdir, f) for f in os.listdir(hdir)] if os.path.isdir(hdir) else []) + [LIB]
+    hdir2 = os.path.join(HERE, "host", "CentroidalMPCWalking")
+    hdeps = host_src + [os.path.join(d, f) for d in (hdir, hdir2) if os.path.isdir(d) for f in os.listdir(d)] + [LIB]
     if host_src and (force or _stale(HOSTLIB, hdeps)):
         inc = os.path.join(os.path.dirname(HERE), "include")
         cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", inc, "-I", os.path.join(HERE, "host"), *host_src, "-o", HOSTLIB,

@@ -50,6 +50,9 @@ def load_host_library() -> C.CDLL:
     L.cmpch_get_trajectories.argtypes = [vp, _dp, _dp, _dp]
     L.cmpch_get_stats.argtypes = [vp, C.POINTER(i), C.POINTER(i), _dp]
     L.cmpch_get_output_contact_list.argtypes = [vp, s, i, _dp, _dp, _dp]
+    L.cmpch_desired_zmp.argtypes = [vp, _dp]
+    L.cmpch_commit_contacts_merged.argtypes = [vp, d, i]
+    L.cmpch_resample_linear.argtypes = [i, _dp, _dp, i, _dp, _dp]
     _host = L
     return L
 
@@ -110,6 +113,22 @@ class CentroidalMPCHost:
                 return False
         return self.lib.cmpch_commit_contacts(self.h, float(force_sample_time)) == 0
 
+    def set_planner_contact_lists(self, lists: dict, force_sample_time: float = 0.0, first_run: bool = False) -> int:
+        """per-tick sequence of the reference's block: planner lists merged with the MPC's own output (updateContactPhaseList)"""
+        for name, contacts in lists.items():
+            n = len(contacts)
+            t_on = np.array([c[0] for c in contacts], dtype=np.float64)
+            t_off = np.array([c[1] for c in contacts], dtype=np.float64)
+            pos = np.array([c[2] for c in contacts], dtype=np.float64).reshape(n, 3)
+            yaw = np.array([c[3] if len(c) > 3 else 0.0 for c in contacts], dtype=np.float64)
+            if self.lib.cmpch_set_contact_list(self.h, name.encode(), n, _p(t_on), _p(t_off), _p(pos), _p(yaw)) != 0:
+                return -3
+        return self.lib.cmpch_commit_contacts_merged(self.h, float(force_sample_time), int(first_run))
+
+    def desired_zmp(self):
+        z = np.zeros(2)
+        return z if self.lib.cmpch_desired_zmp(self.h, _p(z)) == 0 else None
+
     def solver_inputs(self):
         p, lbg, ubg, x0 = np.zeros(self.L.np), np.zeros(self.L.m), np.zeros(self.L.m), np.zeros(self.L.n)
         if self.lib.cmpch_get_inputs(self.h, _p(p), _p(lbg), _p(ubg), _p(x0)) != 0:
@@ -152,6 +171,18 @@ class CentroidalMPCHost:
         t_on, t_off, pos = np.zeros(cap), np.zeros(cap), np.zeros((cap, 3))
         n = self.lib.cmpch_get_output_contact_list(self.h, name.encode(), cap, _p(t_on), _p(t_off), _p(pos))
         return [(t_on[i], t_off[i], pos[i].copy()) for i in range(max(n, 0))]
+
+
+def resample_linear(t_in, p_in, t_out):
+    """CentroidalMPCWalking::resampleLinear (the reference's LinearSpline frequency adapter)"""
+    L = load_host_library()
+    t_in = np.ascontiguousarray(t_in, dtype=np.float64)
+    p_in = np.ascontiguousarray(p_in, dtype=np.float64).reshape(-1, 3)
+    t_out = np.ascontiguousarray(t_out, dtype=np.float64)
+    out = np.zeros((len(t_out), 3))
+    if L.cmpch_resample_linear(len(t_in), _p(t_in), _p(p_in), len(t_out), _p(t_out), _p(out)) != 0:
+        raise ValueError("resampleLinear: inconsistent input")
+    return out
 
 
 def walk_contact_lists(phase: int, dT=0.1, n_steps=12, step_length=0.1, foot_y=0.08, ds_time=0.3, ss_time=0.5, t_past=-100.0):

@@ -7,6 +7,7 @@
 #include <sstream>
 
 #include "BipedalLocomotion/CentroidalMPC.h"
+#include "CentroidalMPCWalking/BlockUtilities.h"
 #include "cmpc_b200.h"
 
 using namespace BipedalLocomotion;
@@ -148,6 +149,35 @@ int cmpch_get_output_contact_list(void* v, const char* name, int cap, double* t_
         ++n;
     }
     return n;
+}
+
+// ZMP of the current output (CentroidalMPCWalking::computeDesiredZMP)
+int cmpch_desired_zmp(void* v, double* zmp2)
+{
+    return CentroidalMPCWalking::computeDesiredZMP(static_cast<Host*>(v)->mpc.getOutput().contacts, zmp2) ? 0 : -1;
+}
+// planner list (pending lists set with cmpch_set_contact_list) merged with the MPC's output list at the controller's
+// current time, then handed to setContactPhaseList: the per-tick sequence of CentroidalMPCBlock::advance()
+int cmpch_commit_contacts_merged(void* v, double force_sample_time, int first_run)
+{
+    Host* h = static_cast<Host*>(v);
+    Contacts::ContactPhaseList planner, merged;
+    planner.setLists(h->pending);
+    if (force_sample_time > 0 && !planner.forceSampleTime(ns(force_sample_time))) return -1;
+    if (first_run) merged = planner;
+    else if (!CentroidalMPCWalking::updateContactPhaseList(h->mpc.currentTime(), planner, h->mpc.getOutput().contactPhaseList, merged)) return -2;
+    return h->mpc.setContactPhaseList(merged) ? 0 : -1;
+}
+// Math::LinearSpline-style resampling: n_in samples (times [s], points 3 n_in) -> n_out points
+int cmpch_resample_linear(int n_in, const double* t_in, const double* p_in, int n_out, const double* t_out, double* p_out)
+{
+    std::vector<std::chrono::nanoseconds> ti(n_in), to(n_out);
+    std::vector<Eigen::Vector3d> pi(n_in), po;
+    for (int i = 0; i < n_in; ++i) { ti[i] = ns(t_in[i]); pi[i] = {p_in[3 * i], p_in[3 * i + 1], p_in[3 * i + 2]}; }
+    for (int i = 0; i < n_out; ++i) to[i] = ns(t_out[i]);
+    if (!CentroidalMPCWalking::resampleLinear(ti, pi, to, po)) return -1;
+    for (int i = 0; i < n_out; ++i) std::memcpy(p_out + 3 * i, po[i].data(), 24);
+    return 0;
 }
 
 }  // extern "C"

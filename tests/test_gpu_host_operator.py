@@ -77,3 +77,39 @@ def test_warm_started_ticks_and_batch(workloads):
     assert sum(its1) <= sum(its0), (its0, its1)
     for m in ms:
         assert abs(m.current_time() - 0.2) < 1e-15
+
+
+def test_block_tick_sequence_with_merged_contact_lists(workloads):
+    """the per-tick sequence of CentroidalMPCBlock::advance(): planner lists merged with the MPC's own (adjusted) current
+    contact (updateContactPhaseList), solve, desired ZMP from the corner forces"""
+    H = pkg("host")
+    phase = 6                                        # right foot in mid swing: it lands inside the horizon
+    m, w = setup(H, workloads, phase=phase, seed=31, noise=1.0)
+    planner = H.walk_contact_lists(phase)
+    assert m.set_planner_contact_lists(planner, force_sample_time=0.1, first_run=True) == 0
+    assert m.advance(), m.last_error()
+    nxt = m.next_planned_contact("right_foot")
+    assert nxt is not None
+    z = m.desired_zmp()
+    posl, Rl, fl = m.contact_output("left_foot")
+    assert z is not None and abs(z[0] - posl[0]) <= 0.08 + 1e-9 and abs(z[1] - posl[1]) <= 0.03 + 1e-9   # single support: ZMP in the left foot
+    # tick until the right foot has landed: from then on the merged list must carry the MPC's adjusted pose, not the planner's
+    landed_pose = None
+    for tick in range(1, 8):
+        com, dcom, h = m.trajectories()
+        assert m.set_state(com[1], dcom[1], h[1])
+        ref = np.vstack([com[1:], com[-1:]])
+        ref[:, 2] = 0.7
+        assert m.set_reference_trajectory(ref, np.zeros((13, 3)))
+        land_plan = m.next_planned_contact("right_foot")
+        if land_plan is not None:
+            landed_pose = land_plan
+        assert m.set_planner_contact_lists(planner, force_sample_time=0.1, first_run=False) == 0, m.last_error()
+        assert m.advance(), m.last_error()
+    assert landed_pose is not None
+    t_now = m.current_time() - 0.1                   # time of the last solve
+    cur = [c for c in m.output_contact_list("right_foot") if c[0] <= t_now + 1e-9 < c[1]]
+    assert len(cur) == 1
+    planned = [c for c in planner["right_foot"] if c[0] <= t_now + 1e-9 < c[1]][0]
+    assert np.allclose(cur[0][2], landed_pose[0], atol=2e-3)            # the MPC's own landing position is kept ...
+    assert abs(cur[0][0] - planned[0]) < 1e-9 and abs(cur[0][1] - planned[1]) < 1e-9   # ... with the planner's timing

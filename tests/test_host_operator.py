@@ -107,3 +107,16 @@ def test_rotation_and_external_wrench_population(H):
     assert np.allclose(lb[L.g_box(1, 8):L.g_box(1, 8) + 3], [-0.01, -0.05, 0.0]) and np.allclose(ub[L.g_box(1, 8):L.g_box(1, 8) + 3], [0.01, 0.0, 0.0])
     # friction rows: one sided
     assert np.all(lb[L.g_fric(0, 0, 0):L.g_fric(0, 0, 0) + 16 * 12] <= -1e19) and np.all(ub[L.g_fric(0, 0, 0):L.g_fric(0, 0, 0) + 16 * 12] == 0)
+
+
+def test_resample_linear_matches_numpy(H):
+    rng = np.random.default_rng(0)
+    t_in = np.arange(0, 60) * 0.02 * 1.5            # 50 Hz planner samples with a slow-down factor
+    p_in = rng.normal(size=(60, 3))
+    t_out = np.arange(0, 13) * 0.1
+    out = H.resample_linear(t_in, p_in, t_out)
+    ref = np.stack([np.interp(t_out, t_in, p_in[:, a]) for a in range(3)], axis=1)
+    assert np.allclose(out, ref, atol=1e-12)
+    assert np.allclose(H.resample_linear(t_in, p_in, [-1.0, 100.0]), [p_in[0], p_in[-1]])   # end points are held
+    with pytest.raises(ValueError):
+        H.resample_linear([0.0, 0.0], p_in[:2], t_out)                                       # times must increase
