@@ -14,7 +14,7 @@ import numpy as np
 from .layout import Layout  # noqa: F401
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcmpc_b200.so")
+LIB_PATH = os.environ.get("CMPC_B200_LIB", os.path.join(HERE, "libcmpc_b200.so"))  # override: A/B builds under profiles/_build
 
 STATUS_NAMES = {0: "converged", 1: "max_iter", 2: "line_search", 3: "numerical", 4: "bad_input"}
 
