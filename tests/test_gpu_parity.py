@@ -241,3 +241,36 @@ def test_plant_rk4(solver12, workloads):
             k1 = fdot(s); k2 = fdot(s + 0.001 * k1); k3 = fdot(s + 0.001 * k2); k4 = fdot(s + 0.002 * k3)
             s = s + 0.002 / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
         assert np.max(np.abs(out[b] - s)) < 1e-12
+
+
+@pytest.mark.parametrize("N", [2, 22, 50])
+def test_solve_other_horizons_match_oracle(oracle, workloads, N):
+    """reference horizons (ergoCubSN001: 22 knots) and the ends of BASELINE's horizon sweep: same optimum as the oracle"""
+    P = pkg()
+    s = P.BatchedCentroidalMPC(P.ergocub_config(horizon=N, contact_position_weight=200.0))
+    w = workloads.walk_batch(N=N, B=6, seed=N, state_noise=1.0, yaw_range=0.2)
+    x, lam, obj, status, iters = s.solve_host(w["p"], w["lbg"], w["ubg"], w["x0"])
+    xo, lo, st = oracle.solve_batch(make_cfg(N=N), w["p"], w["lbg"], w["ubg"], w["x0"], threads=3)
+    L = pkg("layout").Layout(N)
+    for b in range(6):
+        assert status[b] == 0 and st[b].status == 0, (b, status[b], st[b].status)
+        compare_solutions(L, x[b], xo[b], obj[b], st[b].obj)
+    s.close()
+
+
+def test_empty_batch_and_team_sizes(workloads, oracle):
+    """batch of zero instances is a no-op; every team size gives the same solutions"""
+    P = pkg()
+    w = workloads.walk_batch(N=12, B=5, seed=3, state_noise=1.0)
+    ref = None
+    for team in (32, 64, 96, 128):
+        s = P.BatchedCentroidalMPC(P.ergocub_config(contact_position_weight=200.0, threads_per_instance=team))
+        e = torch.empty(0, 1, dtype=torch.float64, device="cuda")
+        assert s.lib.cmpc_solve_batched(s.handle, 0, None, None, None, None, None, None, None, None, 0, None) in (0, -1)
+        x, lam, obj, status, iters = s.solve_host(w["p"], w["lbg"], w["ubg"], w["x0"])
+        assert (status == 0).all()
+        if ref is None:
+            ref = (x, obj)
+        else:
+            assert np.max(np.abs(x - ref[0])) < 1e-6 and np.max(np.abs(obj - ref[1]) / np.abs(ref[1])) < 1e-9
+        s.close()
