@@ -152,6 +152,7 @@ def main():
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--team", type=int, default=0, help="threads per instance (32/64/96/128), 0 = library default")
+    ap.add_argument("--lockstep", type=int, default=0, help="teams per CTA walking in lock-step (1, 3, 7; 0 = library default)")
     ap.add_argument("--identical", action="store_true", help="experiment: every instance is a copy of instance 0")
     ap.add_argument("--ctas", type=int, default=0, help="resident teams per SM (0 = occupancy)")
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (0 = the workload's own size)")
@@ -183,6 +184,7 @@ def main():
     cfg.ipopt_tolerance = args.tol
     cfg.threads_per_instance = args.team
     cfg.ctas_per_sm = args.ctas
+    cfg.teams_per_cta = args.lockstep
     solver = pkg.BatchedCentroidalMPC(cfg)
     B, N = w["p"].shape[0], cfg.horizon
     n, m, npar = solver.L.n, solver.L.m, solver.L.np

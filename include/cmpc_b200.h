@@ -67,6 +67,7 @@ typedef struct cmpc_config {
     int device;                             /* CUDA device ordinal                                                  */
     int threads_per_instance;               /* team size: 32, 64, 96 or 128 threads per instance, 0 = default (96)  */
     int ctas_per_sm;                        /* resident CTAs per SM used to size the persistent grid, 0 = occupancy */
+    int teams_per_cta;                      /* teams walking in lock-step through one CTA: 1, 3 or 7; 0 = default    */
 } cmpc_config;
 
 typedef struct cmpc_handle_s* cmpc_handle;

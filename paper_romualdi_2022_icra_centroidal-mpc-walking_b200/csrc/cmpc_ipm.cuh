@@ -73,7 +73,7 @@ struct EvalStats { double f, theta, phi; };
 // shared memory of one team: the Riccati block first (P at offset 0: 16-byte aligned async copies), then everything the
 // interior-point loop would otherwise keep on the thread stacks.  Local memory is poison here: the shared-memory carve-out
 // leaves almost no L1, so every stack access is an L2 round trip (ncu: as many local loads as global loads, 83 % missing L1).
-struct ISmem {
+struct alignas(16) ISmem {
     WSmem sw;
     WorkS w;                 // array pointers of the instance's scratch block
     SweepIO io;
@@ -81,6 +81,7 @@ struct ISmem {
     StepStats ss;
     EvalStats es;
     double filt_t[MAX_FILTER], filt_p[MAX_FILTER];
+    int inst;                // instance taken from the work queue
 };
 
 // CasADi row of path row l of knot k
@@ -206,9 +207,10 @@ CMPC_FN double hess_dz_entry(const Config& cfg, const WorkS& w, double dw, int k
 
 // ------------------------------------------------------------------------------------------------ evaluation of a point
 // stage data, equality residuals, path row values, objective, theta (l1 infeasibility) and the barrier function at (zsrc, slsrc)
-template <int NT, class Cta>
-CMPC_FN void eval_point(Cta& cta, const Config& cfg, ISmem& sm, const double* zsrc, const double* slsrc, double mu)
+template <int NT, int G, class Cta>
+CMPC_FN void eval_point(Team T, Cta& cta, const Config& cfg, ISmem& sm, const double* zsrc, const double* slsrc, double mu)
 {
+    cta_align<G>();
     const WorkS& w = sm.w;
     const int N = cfg.N;
     const double dT = cfg.dT;
@@ -328,9 +330,10 @@ CMPC_HD double kkt_E(const KktStats& s, double mu, double* compl_out)
 }
 
 // one pass: gradient of f (stored), dual residual, violation, complementarity products, multiplier sums
-template <int NT, class Cta>
-CMPC_FN void kkt_pass(Cta& cta, const Config& cfg, ISmem& sm)
+template <int NT, int G, class Cta>
+CMPC_FN void kkt_pass(Team T, Cta& cta, const Config& cfg, ISmem& sm)
 {
+    cta_align<G>();
     const WorkS& w = sm.w;
     const int N = cfg.N;
     // the values of the off-diagonal non-zeros of A at the iterate (needed by jty_entry and by the adjoint recursion)
@@ -389,9 +392,10 @@ CMPC_FN void kkt_pass(Cta& cta, const Config& cfg, ISmem& sm)
 }
 
 // Sigma and the barrier gradient terms of the path rows, then the small blocks of the Riccati sweep for every knot
-template <int NT>
-CMPC_FN void barrier_pass(const Config& cfg, const WorkS& w, double mu, double dw, double dc)
+template <int NT, int G>
+CMPC_FN void barrier_pass(Team T, const Config& cfg, const WorkS& w, double mu, double dw, double dc)
 {
+    cta_align<G>();
     const int N = cfg.N;
     CMPC_LANES
         {
@@ -472,9 +476,10 @@ CMPC_FN void barrier_pass(const Config& cfg, const WorkS& w, double mu, double d
 
 // eliminated rows of the Newton system from dz (W-B eq. 13), then the multipliers of the equality rows by the adjoint
 // recursion  lambda+_k = A_k' lambda+_{k+1} - [grad f + W dz + sum_box a_i (y_i + dy_i)]_{s_k}  (exact for the given dz)
-template <int NT>
-CMPC_FN void recover_pass(const Config& cfg, const WorkS& w, double mu, double dw, double dc)
+template <int NT, int G>
+CMPC_FN void recover_pass(Team T, const Config& cfg, const WorkS& w, double mu, double dw, double dc)
 {
+    cta_align<G>();
     const int N = cfg.N;
     CMPC_LANES
         for (int it = lane; it < N * 64; it += NT) {
@@ -529,9 +534,7 @@ CMPC_FN void recover_pass(const Config& cfg, const WorkS& w, double mu, double d
             lamp.at(lane) = v;
             if (lane < NS) { w.lamn[N * ES + lane] = v; w.dlam[N * ES + lane] = v - w.lam[N * ES + lane]; }
         CMPC_WARP0_END
-#if defined(__CUDA_ARCH__)
-        if (threadIdx.x < 32)
-#endif
+        CMPC_IF_WARP0
         {
             CMPC_ROLLED
             for (int k = N - 1; k >= 0; --k) {
@@ -550,14 +553,15 @@ CMPC_FN void recover_pass(const Config& cfg, const WorkS& w, double mu, double d
             }
         }
     }
-    team_sync<NT>();
+    team_sync<NT, G>(T);
 }
 
 // residual of the linearised stationarity (right hand side of the refinement) and, for the line search, the fraction to the
 // boundary (eq. 15) and the directional derivative of the barrier function
-template <int NT, class Cta>
-CMPC_FN void step_pass(Cta& cta, const Config& cfg, ISmem& sm, double mu, double dw, double tau)
+template <int NT, int G, class Cta>
+CMPC_FN void step_pass(Team T, Cta& cta, const Config& cfg, ISmem& sm, double mu, double dw, double tau)
 {
+    cta_align<G>();
     const WorkS& w = sm.w;
     const int N = cfg.N;
     double vmax[2] = {0.0, 0.0};    // rho, non-finite flag
@@ -608,27 +612,74 @@ CMPC_FN void step_pass(Cta& cta, const Config& cfg, ISmem& sm, double mu, double
 }
 
 // ------------------------------------------------------------------------------------------------ the solver
-// x_io: in = initial guess, out = solution (CasADi order).  lam_io: multipliers of g (out; in when warm_duals).
-template <int NT, class Cta>
-CMPC_HD Result ipm_solve_team(Cta& cta, const Config& cfg, const Instance& in, double* scratch, ISmem& ism,
-                              const unsigned short* cmap, double* x_io, double* lam_io, int warm_duals)
+// Persistent driver of one team: pulls instances from the work queue and solves them one after the other.  With G > 1
+// teams per CTA the teams run in lock-step: every sub-round (set-up, factorisation retry, refinement, re-evaluation for a
+// new barrier parameter, line-search trial, write-back) is executed by all teams when ANY team needs it (vote_any), the
+// teams that do not need it skip the work inside the phases (T.on) but never a barrier.
+// Batched arrays in the reference's CasADi order, instance major; x: in = initial guess, out = solution; lam: multipliers of g
+// (out; in when warm_duals).
+template <int NT, int G, class Cta>
+CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem& ism, const unsigned short* cmap, int batch,
+                     const double* p_all, const double* lbg_all, const double* ubg_all, double* x_all, double* lam_all,
+                     double* obj_all, int* status_all, int* iters_all, int warm_duals, unsigned int* counter)
 {
-    const int N = cfg.N;
+    const int N = cfg.N, n = dim_x(N), np = dim_p(N), m = dim_g(N);
     WSmem& sm = ism.sw;
     WorkS& w = ism.w;
     SweepIO& io = ism.io;
+    T.on = true;
     CMPC_LANES
         if (lane == 0) {
             works_carve(scratch, N, w);
             io.sd = w.sd; io.small = w.small; io.ric = w.ric; io.ceq = w.ceq; io.dz = w.dz; io.res = w.res; io.cmap = cmap;
         }
     CMPC_LANES_END
-    Result res;
-    res.status = 1; res.iters = 0; res.obj = 0; res.kkt = 0;
-    const bool warm = warm_duals && lam_io;
+    double* filt_t = ism.filt_t;
+    double* filt_p = ism.filt_p;
+    const double mu_min = cfg.tol / (KAPPA_EPS + 1.0);
 
-    // ---- setup: table of constants, rows (classified, bounds relaxed by bound_relax_factor), iterate; validation
-    double bad[1] = {0.0};
+    // state of the instance the team is working on (thread-private copies, uniform over the team)
+    bool alive = true;   // the queue still has work for this team
+    int inst = -1;       // instance index, -1 = none
+    Instance in{nullptr, nullptr, nullptr};
+    double* x_io = nullptr;
+    double* lam_io = nullptr;
+    bool warm = false;
+    double mu = cfg.mu_init, tau = TAU_MIN, f = 0, theta0 = 0, phi0 = 0, theta_max = 0, theta_min = 0, dw_last = 0, E0 = 0;
+    int nfilt = 0, it = 0;
+
+    for (;;) {
+        // ---- work queue: a team without an instance takes the next one
+        const bool want = alive && inst < 0;
+        T.on = want;
+        CMPC_LANES
+            if (lane == 0) {
+#if defined(__CUDA_ARCH__)
+                ism.inst = (int)atomicAdd(counter, 1u);
+#else
+                ism.inst = (int)((*counter)++);
+#endif
+            }
+        CMPC_LANES_END
+        bool fresh = false;
+        if (want) {
+            inst = ism.inst;
+            if (inst >= batch) { alive = false; inst = -1; }
+            else fresh = true;
+        }
+        if (!vote_any<G>(alive)) break;
+        int fin = -1;  // >= 0: the instance is finished with this status at the end of the round
+
+        // ---- set-up of a fresh instance: table of constants, rows (classified, bounds relaxed), iterate; validation
+        if (vote_any<G>(fresh)) {
+            T.on = fresh;
+            if (fresh) {
+                in.p = p_all + (size_t)inst * np; in.lbg = lbg_all + (size_t)inst * m; in.ubg = ubg_all + (size_t)inst * m;
+                x_io = x_all + (size_t)inst * n;
+                lam_io = lam_all ? lam_all + (size_t)inst * m : nullptr;
+                warm = warm_duals && lam_io;
+            }
+            double bad[1] = {0.0};
     CMPC_LANES
         for (int it = lane; it < (N + 1) * 128; it += NT) {
             const int k = it >> 7, r = it & 127;
@@ -701,15 +752,13 @@ CMPC_HD Result ipm_solve_team(Cta& cta, const Config& cfg, const Instance& in, d
             w.dsl[pr] = 0.0; w.dzl[pr] = 0.0; w.dzu[pr] = 0.0; w.dyp[pr] = 0.0; w.ypn[pr] = 0.0; w.slt[pr] = 0.0;
         }
     CMPC_LANES_END_NOSYNC
-    cta.template maxv<1>(bad);
-    team_sync<NT>();
-    if (bad[0] != 0.0) { res.status = 4; return res; }
-
-    // ---- initial point: slacks pushed inside their bounds (bound_push / bound_frac), bound multipliers 1
-    double mu = cfg.mu_init, tau = fmax(TAU_MIN, 1.0 - mu);
-    const double mu_min = cfg.tol / (KAPPA_EPS + 1.0);
-    double f, theta0, phi0;
-    eval_point<NT>(cta, cfg, ism, w.z, w.sl, mu);  // path row values (the slacks are not set yet)
+            cta.template maxv<1>(bad);
+            team_sync<NT, G>(T);
+            if (fresh && bad[0] != 0.0) { fin = 4; fresh = false; f = 0; it = 0; E0 = 0; }
+            // initial point: slacks pushed inside their bounds (bound_push / bound_frac), bound multipliers 1
+            T.on = fresh;
+            if (fresh) { mu = cfg.mu_init; tau = fmax(TAU_MIN, 1.0 - mu); nfilt = 0; dw_last = 0.0; it = 0; }
+            eval_point<NT, G>(T, cta, cfg, ism, w.z, w.sl, mu);  // path row values (the slacks are not set yet)
     CMPC_LANES
         for (int it = lane; it < N * 64; it += NT) {
             const int k = it >> 6, l = it & 63;
@@ -736,77 +785,92 @@ CMPC_HD Result ipm_solve_team(Cta& cta, const Config& cfg, const Instance& in, d
             w.zl[pr] = zl; w.zu[pr] = zu;
         }
     CMPC_LANES_END
-    eval_point<NT>(cta, cfg, ism, w.z, w.sl, mu);
-    f = ism.es.f; theta0 = ism.es.theta; phi0 = ism.es.phi;
-    const double theta_max = 1e4 * fmax(1.0, theta0), theta_min = 1e-4 * fmax(1.0, theta0);
-    double* filt_t = ism.filt_t;
-    double* filt_p = ism.filt_p;
-    int nfilt = 0;
-    double dw_last = 0.0;
-    double E0 = 0.0;
-    int it = 0, status = 1;
+            eval_point<NT, G>(T, cta, cfg, ism, w.z, w.sl, mu);
+            if (fresh) {
+                f = ism.es.f; theta0 = ism.es.theta; phi0 = ism.es.phi;
+                theta_max = 1e4 * fmax(1.0, theta0); theta_min = 1e-4 * fmax(1.0, theta0);
+            }
+        }
 
-    CMPC_TIC
-    CMPC_TOC(0)
-    for (it = 0; it <= cfg.max_iter; ++it) {
-        kkt_pass<NT>(cta, cfg, ism);
+        // ---- one interior-point iteration of every team that holds an instance
+        bool act = alive && inst >= 0 && fin < 0;
+        CMPC_TIC
+        T.on = act;
+        kkt_pass<NT, G>(T, cta, cfg, ism);
         CMPC_TOC(1)
-        const KktStats ks = ism.ks;
-        double cmp0;
-        E0 = kkt_E(ks, 0.0, &cmp0);
-        if (E0 <= cfg.tol && ks.dual <= 1.0 && ks.viol <= 1e-4 && cmp0 <= 1e-4) { status = 0; break; }
-        if (it == cfg.max_iter) { status = 1; break; }
-        // barrier update (eq. 7), filter reset
+        KktStats ks = ism.ks;
         bool mu_changed = false;
-        while (kkt_E(ks, mu, nullptr) <= KAPPA_EPS * mu && mu > mu_min) {
-            mu = fmax(mu_min, fmin(KAPPA_MU * mu, mu * sqrt(mu)));
-            tau = fmax(TAU_MIN, 1.0 - mu);
-            nfilt = 0;
-            mu_changed = true;
+        if (act) {
+            double cmp0;
+            E0 = kkt_E(ks, 0.0, &cmp0);
+            if (E0 <= cfg.tol && ks.dual <= 1.0 && ks.viol <= 1e-4 && cmp0 <= 1e-4) { fin = 0; act = false; }
+            else if (it == cfg.max_iter) { fin = 1; act = false; }
+        }
+        if (act) {
+            // barrier update (eq. 7), filter reset
+            while (kkt_E(ks, mu, nullptr) <= KAPPA_EPS * mu && mu > mu_min) {
+                mu = fmax(mu_min, fmin(KAPPA_MU * mu, mu * sqrt(mu)));
+                tau = fmax(TAU_MIN, 1.0 - mu);
+                nfilt = 0;
+                mu_changed = true;
+            }
         }
         // ---- search direction with inertia correction (alg. IC): Cholesky failure inside the Riccati sweep <=> wrong inertia
         const double dc = fmax(DC_BAR * sqrt(sqrt(mu)), DC_FLOOR);
         double dw = 0.0;
-        int rc = 1, tries = 0;
-        for (;;) {
-            barrier_pass<NT>(cfg, w, mu, dw, dc);
+        int tries = 0;
+        bool needf = act;
+        while (vote_any<G>(needf)) {
+            T.on = needf;
+            barrier_pass<NT, G>(T, cfg, w, mu, dw, dc);
             CMPC_TOC(2)
-            rc = riccati_backward<NT>(cfg, io, sm, dw);
+            const int rc = riccati_backward<NT, G>(T, cfg, io, sm, dw);
             CMPC_TOC(3)
-            if (rc == 0) break;
-            if (dw == 0.0) dw = dw_last == 0.0 ? DW_FIRST : fmax(DW_MIN, KW_MINUS * dw_last);
-            else dw *= (dw_last == 0.0 ? KW_PLUS_FIRST : KW_PLUS);
-            if (dw > DW_MAX || ++tries > 60) break;
+            if (needf) {
+                if (rc == 0) needf = false;
+                else {
+                    if (dw == 0.0) dw = dw_last == 0.0 ? DW_FIRST : fmax(DW_MIN, KW_MINUS * dw_last);
+                    else dw *= (dw_last == 0.0 ? KW_PLUS_FIRST : KW_PLUS);
+                    if (dw > DW_MAX || ++tries > 60) { needf = false; fin = 3; act = false; }
+                }
+            }
         }
-        if (rc != 0) { status = 3; break; }
-        if (dw > 0.0) dw_last = dw;
-        riccati_forward<NT>(cfg, io, sm, false);
+        if (act && dw > 0.0) dw_last = dw;
+        T.on = act;
+        riccati_forward<NT, G>(T, cfg, io, sm, false);
         CMPC_TOC(4)
-        recover_pass<NT>(cfg, w, mu, dw, dc);
+        recover_pass<NT, G>(T, cfg, w, mu, dw, dc);
         CMPC_TOC(5)
-        step_pass<NT>(cta, cfg, ism, mu, dw, tau);
+        step_pass<NT, G>(T, cta, cfg, ism, mu, dw, tau);
         StepStats ss = ism.ss;
         CMPC_TOC(6)
         // ---- iterative refinement on the stationarity residual of the Newton system (the eliminated rows hold exactly)
         double rho_prev = HUGE_VAL;
-        for (int rf = 0; rf < MAX_REFINE; ++rf) {
-            if (!(ss.rho > REFINE_TOL) || ss.rho > 0.5 * rho_prev) break;
-            rho_prev = ss.rho;
-            refine_backward<NT>(cfg, io, sm);
-            riccati_forward<NT>(cfg, io, sm, true);
-            recover_pass<NT>(cfg, w, mu, dw, dc);
-            step_pass<NT>(cta, cfg, ism, mu, dw, tau);
-            ss = ism.ss;
+        int rf = 0;
+        for (;;) {
+            const bool needr = act && rf < MAX_REFINE && ss.rho > REFINE_TOL && !(ss.rho > 0.5 * rho_prev);
+            if (!vote_any<G>(needr)) break;
+            T.on = needr;
+            if (needr) rho_prev = ss.rho;
+            refine_backward<NT, G>(T, cfg, io, sm);
+            riccati_forward<NT, G>(T, cfg, io, sm, true);
+            recover_pass<NT, G>(T, cfg, w, mu, dw, dc);
+            step_pass<NT, G>(T, cta, cfg, ism, mu, dw, tau);
+            if (needr) { ss = ism.ss; ++rf; }
         }
         CMPC_TOC(7)
-        if (ss.bad != 0.0) { status = 3; break; }
+        if (act && ss.bad != 0.0) { fin = 3; act = false; }
         const double amax = ss.amax, az = ss.az, dphi = ss.dphi;
         // ---- filter line search (alg. A)
-        double theta, phi;
-        if (mu_changed || it == 0) {
-            eval_point<NT>(cta, cfg, ism, w.z, w.sl, mu);  // barrier function of the current point for the new mu
-            theta = ism.es.theta; phi = ism.es.phi;
-        } else { theta = theta0; phi = phi0; }
+        double theta = theta0, phi = phi0;
+        {
+            const bool need_eval = act && mu_changed;   // barrier function of the current point for the new mu
+            if (vote_any<G>(need_eval)) {
+                T.on = need_eval;
+                eval_point<NT, G>(T, cta, cfg, ism, w.z, w.sl, mu);
+                if (need_eval) { theta = ism.es.theta; phi = ism.es.phi; }
+            }
+        }
         double amin;
         if (dphi < 0) {
             amin = fmin(GAMMA_THETA, GAMMA_PHI * theta / (-dphi));
@@ -815,7 +879,9 @@ CMPC_HD Result ipm_solve_team(Cta& cta, const Config& cfg, const Instance& in, d
         amin *= GAMMA_ALPHA;
         double alpha = amax, ft = f, th_t = theta, ph_t = phi;
         int accepted = 0, armijo = 0;
-        while (alpha >= amin || alpha == amax) {
+        bool pend = act;
+        while (vote_any<G>(pend)) {
+            T.on = pend;
             CMPC_LANES
                 {
                     double* __restrict__ zt = w.zt; const double* __restrict__ z = w.z; const double* __restrict__ dz = w.dz;
@@ -826,38 +892,42 @@ CMPC_HD Result ipm_solve_team(Cta& cta, const Config& cfg, const Instance& in, d
                     for (int i = lane; i < N * PS; i += NT) slt[i] = sl[i] + alpha * dsl[i];
                 }
             CMPC_LANES_END
-            eval_point<NT>(cta, cfg, ism, w.zt, w.slt, mu);
-            ft = ism.es.f; th_t = ism.es.theta; ph_t = ism.es.phi;
-            bool ok = (fabs(ph_t) < HUGE_VAL) && (fabs(th_t) < HUGE_VAL) && th_t <= theta_max;
-            for (int q = 0; ok && q < nfilt; ++q)
-                if (th_t >= filt_t[q] && ph_t >= filt_p[q]) ok = false;
-            if (ok) {
-                const bool sw = dphi < 0 && theta <= theta_min && alpha * pow(-dphi, S_PHI) > DELTA_SW * pow(theta, S_THETA);
-                const double slack = 10.0 * 2.2e-16 * fabs(phi);
-                if (sw) {
-                    if (ph_t - phi - slack <= ETA_PHI * alpha * dphi) { accepted = 1; armijo = 1; }
-                } else if (th_t <= (1.0 - GAMMA_THETA) * theta || ph_t - slack <= phi - GAMMA_PHI * theta) {
-                    accepted = 1; armijo = 0;
+            eval_point<NT, G>(T, cta, cfg, ism, w.zt, w.slt, mu);
+            if (pend) {
+                ft = ism.es.f; th_t = ism.es.theta; ph_t = ism.es.phi;
+                bool ok = (fabs(ph_t) < HUGE_VAL) && (fabs(th_t) < HUGE_VAL) && th_t <= theta_max;
+                for (int q = 0; ok && q < nfilt; ++q)
+                    if (th_t >= filt_t[q] && ph_t >= filt_p[q]) ok = false;
+                if (ok) {
+                    const bool sw = dphi < 0 && theta <= theta_min && alpha * pow(-dphi, S_PHI) > DELTA_SW * pow(theta, S_THETA);
+                    const double slack = 10.0 * 2.2e-16 * fabs(phi);
+                    if (sw) {
+                        if (ph_t - phi - slack <= ETA_PHI * alpha * dphi) { accepted = 1; armijo = 1; }
+                    } else if (th_t <= (1.0 - GAMMA_THETA) * theta || ph_t - slack <= phi - GAMMA_PHI * theta) {
+                        accepted = 1; armijo = 0;
+                    }
+                }
+                if (accepted) pend = false;
+                else {
+                    alpha *= 0.5;
+                    if (alpha < 1e-16 || !(alpha >= amin)) pend = false;
                 }
             }
-            if (accepted) break;
-            alpha *= 0.5;
-            if (alpha < 1e-16) break;
         }
         CMPC_TOC(8)
-        if (!accepted) { status = 2; break; }  // IPOPT would start its restoration phase here (not restated)
-        if (!armijo && nfilt < MAX_FILTER) {
-            CMPC_LANES
-                if (lane == 0) { filt_t[nfilt] = (1.0 - GAMMA_THETA) * theta; filt_p[nfilt] = phi - GAMMA_PHI * theta; }
-            CMPC_LANES_END_NOSYNC
-            nfilt++;
-        }
-        // ---- accept the trial point (ceq, gp, sd already hold its values): swap the buffers, update the multipliers
-        team_sync<NT>();
+        if (act && !accepted) { fin = 2; act = false; }  // IPOPT would start its restoration phase here (not restated)
+        // ---- accept the trial point (ceq, gp, sd already hold its values): filter, buffer swap, multipliers
+        T.on = act;
         CMPC_LANES
-            if (lane == 0) { double* tmp = w.z; w.z = w.zt; w.zt = tmp; tmp = w.sl; w.sl = w.slt; w.slt = tmp; }
+            if (lane == 0) {
+                if (!armijo && nfilt < MAX_FILTER) { filt_t[nfilt] = (1.0 - GAMMA_THETA) * theta; filt_p[nfilt] = phi - GAMMA_PHI * theta; }
+                double* tmp = w.z; w.z = w.zt; w.zt = tmp; tmp = w.sl; w.sl = w.slt; w.slt = tmp;
+            }
         CMPC_LANES_END
-        f = ft; theta0 = th_t; phi0 = ph_t;
+        if (act) {
+            if (!armijo && nfilt < MAX_FILTER) nfilt++;
+            f = ft; theta0 = th_t; phi0 = ph_t;
+        }
         CMPC_LANES
             {
                 // every load of an item is issued before anything depends on it: one memory round trip per item
@@ -880,8 +950,12 @@ CMPC_HD Result ipm_solve_team(Cta& cta, const Config& cfg, const Instance& in, d
             for (int i = lane; i < (N + 1) * ES; i += NT) w.lam[i] += alpha * w.dlam[i];
         CMPC_LANES_END
         CMPC_TOC(9)
-    }
-    // ---- solution back to the CasADi order
+        if (act) ++it;
+
+        // ---- write-back of the instances that finished in this round (solution to the CasADi order), then back to the queue
+        const bool done = fin >= 0;
+        if (vote_any<G>(done)) {
+            T.on = done && fin != 4;  // rejected input: x is left untouched
     CMPC_LANES
         for (int i2 = lane; i2 < (N + 1) * 64; i2 += NT) {
             const int k = i2 >> 6, r = i2 & 63;
@@ -898,8 +972,16 @@ CMPC_HD Result ipm_solve_team(Cta& cta, const Config& cfg, const Instance& in, d
                 if (l < 38) lam_io[path_row(N, k, l)] = w.yp[k * PS + l];
             }
     CMPC_LANES_END
-    res.status = status; res.iters = it; res.obj = f; res.kkt = E0;
-    return res;
+            if (done) {
+                if (T.lane == 0) {
+                    if (obj_all) obj_all[inst] = f;
+                    if (status_all) status_all[inst] = fin;
+                    if (iters_all) iters_all[inst] = it;
+                }
+                inst = -1;
+            }
+        }
+    }
 }
 
 }  // namespace cmpc

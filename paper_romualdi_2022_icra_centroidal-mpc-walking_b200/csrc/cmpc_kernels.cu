@@ -25,8 +25,10 @@ namespace cmpc {
 // ------------------------------------------------------------------------------------------------ device CTA context
 struct DevCta {
     int tid, nt, warp, lane, wsize;
-    double* red;  // >= 64 doubles of shared memory
-    __device__ __forceinline__ void sync() { __syncthreads(); }
+    int bar = 0;  // hardware barrier of the team (0 = the whole CTA)
+    double* red;  // >= 32 doubles of shared memory
+    __device__ __forceinline__ void bsync() { asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nt) : "memory"); }
+    __device__ __forceinline__ void sync() { bsync(); }
     __device__ __forceinline__ void syncwarp() { __syncwarp(); }
 
     template <int K, class Op>
@@ -42,13 +44,13 @@ struct DevCta {
         const int nw = nt >> 5;
         if (lane == 0)
             for (int k = 0; k < K; ++k) red[warp * K + k] = v[k];
-        __syncthreads();
+        bsync();
         for (int k = 0; k < K; ++k) {
             double x = red[k];
             for (int w2 = 1; w2 < nw; ++w2) x = op(x, red[w2 * K + k]);
             v[k] = x;
         }
-        __syncthreads();
+        bsync();
     }
     template <int K> __device__ __forceinline__ void sumv(double* v) { allreduce<K>(v, [](double a, double b) { return a + b; }); }
     template <int K> __device__ __forceinline__ void maxv(double* v) { allreduce<K>(v, [](double a, double b) { return fmax(a, b); }); }
@@ -68,7 +70,7 @@ struct DevCta {
             const double x = warp_reduce_op(*src, op);
             if (lane == 0) red[warp * K + k] = x;
         }
-        __syncthreads();
+        bsync();
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int op = k < KM ? 0 : (k < KM + KN ? 1 : 2);
@@ -77,7 +79,7 @@ struct DevCta {
             for (int w2 = 1; w2 < nw; ++w2) x = combine_op(x, red[w2 * K + k], op);
             *dst = x;
         }
-        __syncthreads();
+        bsync();
     }
     static __device__ __forceinline__ double combine_op(double x, double y, int op)
     {
@@ -134,38 +136,29 @@ struct DevWarp {
 // THE hot path: persistent CTAs of NT threads (a "team": 1, 2 or 4 warps), one MPC instance per team at a time (atomic work
 // queue).  The whole interior-point solve of the instance runs inside the team: Riccati factorisation on 3 x 3 tiles in
 // shared memory (cmpc_warp.cuh), iterate vectors in a per-team scratch block that stays in L2.
-template <int NT> struct TeamCta { using type = DevCta; };
-template <> struct TeamCta<32> { using type = DevWarp; };
+template <int NT, int G> struct TeamCta { using type = DevCta; };
+template <> struct TeamCta<32, 1> { using type = DevWarp; };
 
-template <int NT, int CTAS>
-__global__ void __launch_bounds__(NT, CTAS)
+// G teams of NT threads per CTA, walking through the phases of their solves in lock-step (cmpc_ipm.cuh: ipm_run)
+template <int NT, int G, int CTAS>
+__global__ void __launch_bounds__(NT * G, CTAS)
 cmpc_solve_team_kernel(const __grid_constant__ Config cfg, int batch, const double* __restrict__ p,
                        const double* __restrict__ lbg, const double* __restrict__ ubg, double* x, double* lam, double* obj,
                        int* status, int* iters, int warm_duals, double* work, size_t work_stride, unsigned int* counter,
                        const unsigned short* __restrict__ cmap)
 {
     extern __shared__ __align__(16) double smem_raw[];
-    ISmem& sm = *reinterpret_cast<ISmem*>(smem_raw);
-    __shared__ int s_inst;
-    typename TeamCta<NT>::type cta;
-    cta.tid = threadIdx.x; cta.nt = NT; cta.warp = threadIdx.x >> 5; cta.lane = threadIdx.x & 31; cta.wsize = 32;
-    if constexpr (NT != 32) cta.red = sm.sw.red;
-    const int N = cfg.N, n = dim_x(N), np = dim_p(N), m = dim_g(N);
-    double* base = work + (size_t)blockIdx.x * work_stride;
-    for (;;) {
-        if (threadIdx.x == 0) s_inst = (int)atomicAdd(counter, 1u);
-        team_sync<NT>();
-        const int inst = s_inst;
-        team_sync<NT>();
-        if (inst >= batch) break;
-        Instance in{p + (size_t)inst * np, lbg + (size_t)inst * m, ubg + (size_t)inst * m};
-        Result r = ipm_solve_team<NT>(cta, cfg, in, base, sm, cmap, x + (size_t)inst * n, lam ? lam + (size_t)inst * m : nullptr, warm_duals);
-        if (threadIdx.x == 0) {
-            if (obj) obj[inst] = r.obj;
-            if (status) status[inst] = r.status;
-            if (iters) iters[inst] = r.iters;
-        }
-    }
+    const int team = threadIdx.x / NT;
+    Team T;
+    T.lane = threadIdx.x - team * NT;
+    T.id = team;
+    T.on = true;
+    ISmem& sm = reinterpret_cast<ISmem*>(smem_raw)[team];
+    typename TeamCta<NT, G>::type cta;
+    cta.tid = T.lane; cta.nt = NT; cta.warp = T.lane >> 5; cta.lane = T.lane & 31; cta.wsize = 32;
+    if constexpr (!(NT == 32 && G == 1)) { cta.red = sm.sw.red; cta.bar = G > 1 ? team + 1 : 0; }
+    double* base = work + ((size_t)blockIdx.x * G + team) * work_stride;
+    ipm_run<NT, G>(T, cta, cfg, base, sm, cmap, batch, p, lbg, ubg, x, lam, obj, status, iters, warm_duals, counter);
 }
 
 // warm-start shift: one CTA per instance, the vector is staged in shared memory so that loads and stores are coalesced
@@ -370,19 +363,26 @@ using namespace cmpc;
 #ifndef CMPC_CTAS_PER_SM
 #define CMPC_CTAS_PER_SM 7
 #endif
-static const void* team_kernel(int nt)
+#ifndef CMPC_DEFAULT_LOCKSTEP
+#define CMPC_DEFAULT_LOCKSTEP 7   // teams per CTA of the default (team 96) configuration; 1 = independent teams
+#endif
+static_assert(sizeof(ISmem) % 16 == 0, "teams of a CTA are laid out back to back in shared memory");
+// (team size, teams per CTA) -> kernel
+#define CMPC_FOR_EACH_KERNEL(X) X(32, 1, CMPC_CTAS_PER_SM) X(64, 1, CMPC_CTAS_PER_SM) X(96, 1, CMPC_CTAS_PER_SM) \
+    X(128, 1, CMPC_CTAS_PER_SM) X(96, 7, 1) X(96, 3, 2) X(64, 7, 1) X(128, 7, 1)
+static const void* team_kernel(int nt, int g)
 {
-    if (nt == 32) return (const void*)cmpc_solve_team_kernel<32, CMPC_CTAS_PER_SM>;
-    if (nt == 64) return (const void*)cmpc_solve_team_kernel<64, CMPC_CTAS_PER_SM>;
-    if (nt == 96) return (const void*)cmpc_solve_team_kernel<96, CMPC_CTAS_PER_SM>;
-    return (const void*)cmpc_solve_team_kernel<128, CMPC_CTAS_PER_SM>;
+#define X(NT, G, C) if (nt == NT && g == G) return (const void*)cmpc_solve_team_kernel<NT, G, C>;
+    CMPC_FOR_EACH_KERNEL(X)
+#undef X
+    return nullptr;
 }
 
 struct cmpc_handle_s {
     Config cfg;
     cmpc_config user;
-    int device = 0, sm_count = 0, threads = CMPC_DEFAULT_TEAM, ctas_per_sm = 0, grid = 0, smem = 0;
-    size_t work_stride = 0;
+    int device = 0, sm_count = 0, lockstep = 1, threads = CMPC_DEFAULT_TEAM, ctas_per_sm = 0, grid = 0, smem = 0;
+    size_t work_stride = 0, work_slots = 0;
     double* d_work = nullptr;
     unsigned int* d_counter = nullptr;
     int *d_jslot = nullptr, *d_hslot = nullptr;
@@ -487,14 +487,15 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, h->device);
     if (e != cudaSuccess) { delete h; return CMPC_E_CUDA; }
     h->sm_count = prop.multiProcessorCount;
-    // threads_per_instance: team size, 32 / 64 / 128 (0 = default)
+    // threads_per_instance: team size (0 = default); teams_per_cta: teams walking in lock-step through one CTA (0 = default)
     h->threads = u->threads_per_instance == 0 ? CMPC_DEFAULT_TEAM : u->threads_per_instance;
-    if (h->threads != 32 && h->threads != 64 && h->threads != 96 && h->threads != 128) { delete h; return CMPC_E_INVALID; }
-    h->smem = (int)sizeof(ISmem);
-    const void* kfn = team_kernel(h->threads);
+    h->lockstep = u->teams_per_cta == 0 ? (u->threads_per_instance == 0 ? CMPC_DEFAULT_LOCKSTEP : 1) : u->teams_per_cta;
+    const void* kfn = team_kernel(h->threads, h->lockstep);
+    if (!kfn) { delete h; return CMPC_E_INVALID; }
+    h->smem = (int)sizeof(ISmem) * h->lockstep;
     int occ = 0;
     e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, h->threads, h->smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, h->threads * h->lockstep, h->smem);
     if (e != cudaSuccess || occ < 1) { h->last_cuda = (int)e; delete h; return CMPC_E_CUDA; }
     h->ctas_per_sm = (u->ctas_per_sm > 0 && u->ctas_per_sm < occ) ? u->ctas_per_sm : occ;
     if (h->ctas_per_sm < occ) {  // fewer resident teams than fit: give the rest of the shared-memory carve-out back to L1
@@ -504,10 +505,11 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
     }
     h->grid = h->sm_count * h->ctas_per_sm;  // persistent grid: a multiple of the SM count
     h->work_stride = ((size_t)works_doubles(c.N) + 15) & ~(size_t)15;
+    h->work_slots = (size_t)h->grid * h->lockstep;
     Csc jc, hc;
     build_csc(c.N, false, jc);
     build_csc(c.N, true, hc);
-    if (cudaMalloc(&h->d_work, sizeof(double) * h->work_stride * h->grid) != cudaSuccess ||
+    if (cudaMalloc(&h->d_work, sizeof(double) * h->work_stride * h->work_slots) != cudaSuccess ||
         cudaMalloc(&h->d_counter, sizeof(unsigned int)) != cudaSuccess ||
         cudaMalloc(&h->d_jslot, sizeof(int) * jc.slot.size()) != cudaSuccess ||
         cudaMalloc(&h->d_hslot, sizeof(int) * hc.slot.size()) != cudaSuccess ||
@@ -516,7 +518,7 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
         cmpc_destroy(h);
         return CMPC_E_ALLOC;
     }
-    cudaMemset(h->d_work, 0, sizeof(double) * h->work_stride * h->grid);
+    cudaMemset(h->d_work, 0, sizeof(double) * h->work_stride * h->work_slots);
     {
         std::vector<unsigned short> cm(CF_DINV);
         build_cmap(cm.data());
@@ -548,16 +550,14 @@ int cmpc_solve_batched(cmpc_handle h, int batch, const double* d_p, const double
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(h->device));
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
-    int grid = std::min(batch, h->grid);
-#define CMPC_LAUNCH_TEAM(NT)                                                                                                  \
-    cmpc_solve_team_kernel<NT, CMPC_CTAS_PER_SM><<<grid, NT, h->smem, st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj, \
-                                                                            d_status, d_iters, warm_duals, h->d_work,        \
-                                                                            h->work_stride, h->d_counter, h->d_cmap)
-    if (h->threads == 32) CMPC_LAUNCH_TEAM(32);
-    else if (h->threads == 64) CMPC_LAUNCH_TEAM(64);
-    else if (h->threads == 96) CMPC_LAUNCH_TEAM(96);
-    else CMPC_LAUNCH_TEAM(128);
-#undef CMPC_LAUNCH_TEAM
+    int grid = std::min((batch + h->lockstep - 1) / h->lockstep, h->grid);
+#define X(NT, G, C)                                                                                                      \
+    if (h->threads == NT && h->lockstep == G)                                                                            \
+        cmpc_solve_team_kernel<NT, G, C><<<grid, NT * G, h->smem, st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj, \
+                                                                        d_status, d_iters, warm_duals, h->d_work,         \
+                                                                        h->work_stride, h->d_counter, h->d_cmap);
+    CMPC_FOR_EACH_KERNEL(X)
+#undef X
     h->launches++;
     CK(cudaGetLastError());
     return CMPC_OK;

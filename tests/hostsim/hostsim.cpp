@@ -46,12 +46,14 @@ static int solve_team(const cmpc::Config* cfg, const double* p, const double* lb
     HostCta cta;
     std::vector<double> buf(cmpc::works_doubles(cfg->N), 0.0);
     static cmpc::ISmem sm;
-    cmpc::Instance in{p, lbg, ubg};
     static unsigned short cmap[cmpc::CF_DINV];
     cmpc::build_cmap(cmap);
-    cmpc::Result r = cmpc::ipm_solve_team<NT>(cta, *cfg, in, buf.data(), sm, cmap, x, lam, warm_duals);
-    *iters = r.iters; *obj = r.obj; *kkt = r.kkt;
-    return r.status;
+    unsigned int counter = 0;
+    int st = -1;
+    cmpc::Team T{0, 0, true};
+    cmpc::ipm_run<NT, 1>(T, cta, *cfg, buf.data(), sm, cmap, 1, p, lbg, ubg, x, lam, obj, &st, iters, warm_duals, &counter);
+    *kkt = 0.0;
+    return st;
 }
 extern "C" int hostsim_solve_team32(const cmpc::Config* cfg, const double* p, const double* lbg, const double* ubg, double* x,
                                     double* lam, int warm_duals, int* iters, double* obj, double* kkt)
