@@ -75,3 +75,17 @@ for f, n in by_func.most_common(25):
 print("---- by line (samples %)")
 for k, s in samp_line.most_common(top):
     print(f"{k[0]}:{k[1]:<5d} samples {100*s/max(tot_s,1):5.2f}%  instr {100*by_line[k]/tot_i:5.2f}%")
+print("---- by line (instr %)")
+for k, n in by_line.most_common(top):
+    print(f"{k[0]}:{k[1]:<5d} instr {100*n/tot_i:5.2f}%  samples {100*samp_line[k]/max(tot_s,1):5.2f}%")
+# optional phase table: CMPC_PHASES="file:lo-hi=name,..."
+ph = os.environ.get("CMPC_PHASES")
+if ph:
+    print("---- by phase (instr %, samples %)")
+    for item in ph.split(","):
+        rng, name = item.split("=")
+        fn, lh = rng.split(":")
+        lo, hi = map(int, lh.split("-"))
+        n = sum(v for (f, l), v in by_line.items() if f == fn and lo <= l <= hi)
+        s = sum(v for (f, l), v in samp_line.items() if f == fn and lo <= l <= hi)
+        print(f"{name:28s} {100*n/tot_i:6.2f}% {100*s/max(tot_s,1):6.2f}%")
