@@ -14,7 +14,7 @@ DEPS.append(os.path.join(os.path.dirname(HERE), "include", "cmpc_b200.h"))
 HOST_SOURCES = [os.path.join(HERE, "host", f) for f in ("CentroidalMPC.cpp", "IniParametersHandler.cpp", "Contacts.cpp", "BlockUtilities.cpp", "capi.cpp")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
-              "--extended-lambda", "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550"]
+              "--extended-lambda", "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "550,177"]
 
 
 def _nvcc() -> str:

@@ -58,6 +58,9 @@ def func_of(file, ln):
     return best
 
 
+STALLS = ["stall_barrier", "stall_long_sb", "stall_short_sb", "stall_wait", "stall_selected", "stall_branch_resolving", "stall_no_inst", "stall_math", "stall_mio", "stall_lg", "stall_not_selected"]
+sidx = [hdr.index(s_) if s_ in hdr else None for s_ in STALLS]
+stall_line = collections.defaultdict(lambda: [0] * len(STALLS))
 by_line, by_func = collections.Counter(), collections.Counter()
 samp_line, samp_func = collections.Counter(), collections.Counter()
 tot_i = tot_s = 0
@@ -65,6 +68,9 @@ for (ln, txt), r in zip(seq, data):
     n = int(float(r[ci] or 0)); s = int(float(r[cs] or 0))
     key = ln or ("?", 0)
     by_line[key] += n; samp_line[key] += s
+    for q, ix in enumerate(sidx):
+        if ix is not None and r[ix]:
+            stall_line[key][q] += int(float(r[ix]))
     f = func_of(*key)
     by_func[f] += n; samp_func[f] += s
     tot_i += n; tot_s += s
@@ -81,11 +87,12 @@ for k, n in by_line.most_common(top):
 # optional phase table: CMPC_PHASES="file:lo-hi=name,..."
 ph = os.environ.get("CMPC_PHASES")
 if ph:
-    print("---- by phase (instr %, samples %)")
+    print("---- by phase (instr %, samples %) | samples % by stall: " + " ".join(x.replace("stall_", "") for x in STALLS))
     for item in ph.split(","):
         rng, name = item.split("=")
         fn, lh = rng.split(":")
         lo, hi = map(int, lh.split("-"))
         n = sum(v for (f, l), v in by_line.items() if f == fn and lo <= l <= hi)
         s = sum(v for (f, l), v in samp_line.items() if f == fn and lo <= l <= hi)
-        print(f"{name:28s} {100*n/tot_i:6.2f}% {100*s/max(tot_s,1):6.2f}%")
+        st = [sum(v[q] for (f, l), v in stall_line.items() if f == fn and lo <= l <= hi) for q in range(len(STALLS))]
+        print(f"{name:28s} {100*n/tot_i:6.2f}% {100*s/max(tot_s,1):6.2f}%  | " + " ".join(f"{100*x/max(tot_s,1):5.2f}" for x in st))
