@@ -11,8 +11,6 @@
 //     primal / complementarity residuals; the barrier-parameter loop needs no second pass because max |s z - mu| follows from
 //     max and min of the products), one barrier pass (Sigma, barrier gradients, the small blocks of the Riccati sweep), one
 //     step pass (eliminated rows, fraction to the boundary, directional derivative), one evaluation pass per trial point;
-//   * every pass streams over the knots: what it reads is staged knot by knot with cp.async into shared-memory rings (on top
-//     of the Riccati workspace, dead outside the sweeps), so the items never wait on L2 / HBM ("knot rings" below);
 //   * the adjoint recursion for the dynamics multipliers is a 16-step shuffle chain on one warp.
 // The linear algebra (Riccati sweeps on 3 x 3 tiles) is in cmpc_warp.cuh.
 #pragma once
@@ -28,6 +26,13 @@ namespace cmpc {
 #define CMPC_UNROLL2
 #define CMPC_UNROLL4
 #endif
+
+// Item loops of the element-wise passes, ROLE MAJOR: the lanes of a warp take consecutive roles (a variable, a row, ...) and
+// the warps of the team split the knots, so that the decoding of a role (divisions, corner / axis indices, table offsets) is
+// invariant in the inner loop over the knots and hoisted out of it, the knot index is uniform over the warp, and the loads of
+// consecutive knots are independent of each other (the passes are bound by their instruction count: profiles/r1_notes.md)
+#define CMPC_ROLES(nroles) for (int r = lane & 31; r < (nroles); r += 32)
+#define CMPC_KNOTS(kfirst, klast) for (int k = (kfirst) + (lane >> 5); k <= (klast); k += (NT >= 32 ? NT / 32 : 1))
 
 constexpr int PS = 40;  // stride of a knot in the path-row arrays: friction 0..31 (16 c + 4 j + r) | step box 32..37 (32 + 3 c + q) | pad
 // per-knot table of constants
@@ -75,12 +80,6 @@ struct EvalStats { double f, theta, phi; };
 // shared memory of one team: the Riccati block first (P at offset 0: 16-byte aligned async copies), then everything the
 // interior-point loop would otherwise keep on the thread stacks.  Local memory is poison here: the shared-memory carve-out
 // leaves almost no L1, so every stack access is an L2 round trip (ncu: as many local loads as global loads, 83 % missing L1).
-struct Seg {           // one staged array of a streamed pass (see "knot rings" below)
-    const double* g;   // global array
-    int roff, stride;  // offset of its ring in the ring area, doubles per knot (global and ring)
-    int len2, nk;      // 16-byte chunks copied per knot, number of knots the array has
-};
-constexpr int MAX_SEG = 18;
 struct alignas(16) ISmem {
     WSmem sw;
     WorkS w;                 // array pointers of the instance's scratch block
@@ -90,8 +89,6 @@ struct alignas(16) ISmem {
     EvalStats es;
     double filt_t[MAX_FILTER], filt_p[MAX_FILTER];
     int inst;                // instance taken from the work queue
-    int nseg;                // segments of the running pass
-    Seg segs[MAX_SEG];
 };
 
 // CasADi row of path row l of knot k
@@ -101,82 +98,9 @@ CMPC_HD int path_row(int N, int k, int l)
     const int q = l - 32;
     return g_box(N, q / 3, k) + q % 3;
 }
-
-// ------------------------------------------------------------------------------------------------ knot rings
-// The element-wise passes of an iteration touch every per-instance vector once; the vectors live in the team's scratch block
-// in global memory (L2 / HBM: 1036 resident teams x 145 KB do not fit the L2), and a pass that loads them where it needs
-// them pays a DRAM round trip per dependent access (ncu: long_scoreboard was the first stall of these passes, 50-70 k cycles
-// per pass for work worth 3 k).  Every pass therefore STREAMS over the knots: the arrays it reads are staged knot by knot
-// with cp.async into 4-slot rings (slot = knot & 3: knots k - 1, k, k + 1 for the stage being processed, k + 2 in flight) that
-// live on top of the Riccati workspace (P, K, ... are dead outside the sweeps); the items of a knot then read shared
-// memory only.  Results go to global memory (and into a ring when a later stage of the same pass needs them).
-constexpr int RING_SLOTS = 4;
-CMPC_HD int kr(int k) { return k & (RING_SLOTS - 1); }
-constexpr int RING_CAP = (int)(offsetof(WSmem, sb) / sizeof(double));  // 3517 doubles (every ring offset is even: 16-byte chunks)
-
-CMPC_HD void async16(double* dst, const double* src)
-{
-#if defined(__CUDA_ARCH__)
-    const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(src));
-#else
-    dst[0] = src[0]; dst[1] = src[1];
-#endif
-}
-// segment s of the running pass: knot k of the global array g (knot stride `stride` doubles, 2 * len2 of them copied) goes to
-// ring + roff + kr(k) * stride
-CMPC_HD void ring_seg(ISmem& sm, int s, const double* g, int roff, int stride, int len2, int nk)
-{
-    Seg& sg = sm.segs[s];
-    sg.g = g; sg.roff = roff; sg.stride = stride; sg.len2 = len2; sg.nk = nk;
-}
-// copies of knot k (the segments are split over the warps of the team)
-template <int NT>
-CMPC_HD void ring_stage(const ISmem& sm, double* ring, int k, int lane)
-{
-    constexpr int NW = NT / 32;
-    const int nseg = sm.nseg;
-    if (k < 0) return;
-    CMPC_ROLLED
-    for (int s = lane >> 5; s < nseg; s += NW) {
-        const Seg& sg = sm.segs[s];
-        if (k >= sg.nk) continue;
-        const double* src = sg.g + (size_t)k * sg.stride;
-        double* dst = ring + sg.roff + kr(k) * sg.stride;
-        for (int i = lane & 31; i < sg.len2; i += 32) async16(dst + 2 * i, src + 2 * i);
-    }
-}
-// the stages kfirst .. klast of a pass: body(k, lane) may read the slots of knots k - 1, k, k + 1 and write the slot of knot k
-// (arrays that are not staged).  One team barrier per stage.
-#define CMPC_RING_PASS_BEGIN(kfirst, klast)                                                      \
-    {                                                                                            \
-        double* const ring = sm.sw.P;                                                            \
-        const int ring_k0 = (kfirst), ring_k1 = (klast);                                         \
-        team_sync<NT, G>(T); /* the segment table is visible, the previous user of the ring is done */ \
-        CMPC_LANES                                                                               \
-            ring_stage<NT>(sm, ring, ring_k0 - 1, lane);                                         \
-            ring_stage<NT>(sm, ring, ring_k0, lane);                                             \
-            ring_stage<NT>(sm, ring, ring_k0 + 1, lane);                                         \
-            async_commit();                                                                      \
-        CMPC_LANES_END_NOSYNC                                                                    \
-        CMPC_ROLLED                                                                              \
-        for (int k = ring_k0; k <= ring_k1; ++k) {                                               \
-            CMPC_LANES                                                                           \
-                async_wait<0>();                                                                 \
-            CMPC_LANES_END                                                                       \
-            CMPC_LANES                                                                           \
-                ring_stage<NT>(sm, ring, k + 2, lane);                                           \
-                async_commit();
-#define CMPC_RING_PASS_END                                                                       \
-            CMPC_LANES_END_NOSYNC                                                                \
-        }                                                                                        \
-        CMPC_LANES                                                                               \
-            async_wait<0>();                                                                     \
-        CMPC_LANES_END                                                                           \
-    }
-
-// value  a' v  of path row l for variables zk (knot k) / zk1 (knot k + 1): jacobian row applied to a step
-CMPC_HD double path_dot(const double* tab, const double* zk, const double* zk1, int l)
+// value  a' v  of path row l of knot k for variables taken from zk (knot k) / zk1 (knot k + 1); sub = 1 subtracts the nominal
+// position (row value), sub = 0 gives the jacobian row applied to a step
+CMPC_HD double path_dot(const double* tab, const double* zk, const double* zk1, int l, int sub)
 {
     if (l < 32) {
         const int c = l >> 4, j = (l >> 2) & 3, r = l & 3;
@@ -187,17 +111,18 @@ CMPC_HD double path_dot(const double* tab, const double* zk, const double* zk1, 
     const int q = l - 32, c = q / 3, qq = q - 3 * c;
     const double* rc = tab + T_R + 9 * c + 3 * qq;  // column qq of R_c
     const double* pos = zk1 + 9 + 3 * c;
+    const double* nom = tab + T_NOM1 + 3 * c;
     double v = 0.0;
-    for (int a = 0; a < 3; ++a) v += rc[a] * pos[a];
+    for (int a = 0; a < 3; ++a) v += rc[a] * (pos[a] - (sub ? nom[a] : 0.0));
     return v;
 }
 
-// gradient of the objective in variable v (0..44) of knot k at the point held by the ring rz (rtab: ring of the tables)
-CMPC_FN double grad_entry(const Config& cfg, const double* rtab, const double* rz, int k, int v)
+// gradient of the objective in variable v (0..44) of knot k at the point zsrc
+CMPC_HD double grad_entry(const Config& cfg, const WorkS& w, const double* zsrc, int k, int v)
 {
     const int N = cfg.N;
-    const double* t = rtab + kr(k) * TS;
-    const double* zk = rz + kr(k) * ZS;
+    const double* t = w.tab + k * TS;
+    const double* zk = zsrc + k * ZS;
     if (v < NS) {
         if (v < 2) return 2.0 * cfg.w_com[v] * (zk[v] - t[T_CREF + v]);
         if (v == 2) return 2.0 * t[T_OM2] * (zk[2] - t[T_CREF + 2]);
@@ -212,62 +137,59 @@ CMPC_FN double grad_entry(const Config& cfg, const double* rtab, const double* r
     const double* fc = zk + NS + 6 + 12 * c + a;  // corner j at fc[3 j]
     const double own = zk[v], sum = fc[0] + fc[3] + fc[6] + fc[9], mean = en / NJ * sum, d = own - mean;
     double g = 2.0 * cfg.w_sym * (d - (en / NJ) * (sum - NJ * mean));
-    if (k + 1 < N) g -= 2.0 * cfg.w_rate[a] * (rz[kr(k + 1) * ZS + v] - own);
-    if (k > 0) g += 2.0 * cfg.w_rate[a] * (own - rz[kr(k - 1) * ZS + v]);
+    if (k + 1 < N) g -= 2.0 * cfg.w_rate[a] * (zsrc[(k + 1) * ZS + v] - own);
+    if (k > 0) g += 2.0 * cfg.w_rate[a] * (own - zsrc[(k - 1) * ZS + v]);
     return g;
 }
 
-// (J' y)[variable v of knot k] for multipliers rlam (equality rows) and ryp (path rows); all arguments are rings
-CMPC_FN double jty_entry(const Config& cfg, const double* rtab, const double* rsd, const double* raw, const double* rlam,
-                         const double* ryp, int k, int v)
+// (J' y)[variable v of knot k] for multipliers lam (equality rows, stage major) and yp (path rows); needs sd / aw at the iterate
+CMPC_HD double jty_entry(const Config& cfg, const WorkS& w, const double* lam, const double* yp, int k, int v)
 {
     const int N = cfg.N;
     if (v < NS) {
         const int i = v;
-        double r = rlam[kr(k) * ES + i];
+        double r = lam[k * ES + i];
         if (k < N) {
-            const double* y1 = rlam + kr(k + 1) * ES;
-            const double* aw = raw + kr(k) * AWS;
+            const double* y1 = lam + (k + 1) * ES;
             int rr[2];
             acol_rows(i, rr);
-            r -= y1[i] + aw[2 * i] * y1[rr[0]] + aw[2 * i + 1] * y1[rr[1]];
+            r -= y1[i] + w.aw[k * AWS + 2 * i] * y1[rr[0]] + w.aw[k * AWS + 2 * i + 1] * y1[rr[1]];
         }
         if (k > 0 && i >= 9) {
             const int c = (i - 9) / 3, a = (i - 9) % 3;
-            const double* R = rtab + kr(k - 1) * TS + T_R + 9 * c;
-            const double* yb = ryp + kr(k - 1) * PS + 32 + 3 * c;
+            const double* R = w.tab + (k - 1) * TS + T_R + 9 * c;
+            const double* yb = yp + (k - 1) * PS + 32 + 3 * c;
             r += R[a] * yb[0] + R[3 + a] * yb[1] + R[6 + a] * yb[2];
         }
         return r;
     }
     const int u = v - NS;
-    const double* t = rtab + kr(k) * TS;
-    const double* y1 = rlam + kr(k + 1) * ES;
+    const double* t = w.tab + k * TS;
+    const double* y1 = lam + (k + 1) * ES;
     if (u < 6) return -t[T_OMD + u / 3] * y1[9 + u];
     const int f = u - 6, c = f / 12, j = (f % 12) / 3, a = f % 3, a1 = (a + 1) % 3, a2 = (a + 2) % 3;
-    const double* rho = rsd + kr(k) * SD_STRIDE + SD_RHO + 3 * (4 * c + j);
+    const double* rho = w.sd + k * SD_STRIDE + SD_RHO + 3 * (4 * c + j);
     double r = -cfg.dT * t[T_EN + c] * (y1[3 + a] + y1[6 + a1] * rho[a2] - y1[6 + a2] * rho[a1]);
     const double* ar = t + T_AR + 12 * c + a;  // row q at ar[3 q]
-    const double* yf = ryp + kr(k) * PS + 16 * c + 4 * j;
+    const double* yf = yp + k * PS + 16 * c + 4 * j;
     r += ar[0] * yf[0] + ar[3] * yf[1] + ar[6] * yf[2] + ar[9] * yf[3];
     return r;
 }
 
-// (W dz)[variable v of knot k]: hessian of the lagrangian (nlp_hess_l, tmp.c:58926) + delta_w I, times the step (rings)
-CMPC_FN double hess_dz_entry(const Config& cfg, const double* rtab, const double* rdz, const double* rlam, const double* rdfc,
-                             double dw, int k, int v)
+// (W dz)[variable v of knot k]: hessian of the lagrangian (nlp_hess_l, tmp.c:58926) + delta_w I, times the step
+CMPC_HD double hess_dz_entry(const Config& cfg, const WorkS& w, double dw, int k, int v)
 {
     const int N = cfg.N;
-    const double* t = rtab + kr(k) * TS;
-    const double* dzk = rdz + kr(k) * ZS;
+    const double* t = w.tab + k * TS;
+    const double* dzk = w.dz + k * ZS;
     if (v < NS) {
         const int i = v;
         double q = i < 2 ? 2.0 * cfg.w_com[i] : i == 2 ? 2.0 * t[T_OM2] : i < 6 ? 0.0 : i < 9 ? 2.0 * cfg.w_h : 2.0 * cfg.w_pos;
         double r = (q + dw) * dzk[i];
         if (k < N && (i < 3 || i >= 9)) {  // bilinear block between forces and com / pos: dT en [lam_h]x
-            const double* lamh = rlam + kr(k + 1) * ES + 6;
+            const double* lamh = w.lam + (k + 1) * ES + 6;
             const int a = i < 3 ? i : (i - 9) % 3, a1 = (a + 1) % 3, a2 = (a + 2) % 3;
-            const double* dF = rdfc + kr(k) * 8;
+            const double* dF = w.dfc + k * 8;
             double acc;
             if (i < 3) acc = t[T_EN] * (dF[a1] * lamh[a2] - dF[a2] * lamh[a1]) + t[T_EN + 1] * (dF[3 + a1] * lamh[a2] - dF[3 + a2] * lamh[a1]);
             else { const int c = (i - 9) / 3; acc = -t[T_EN + c] * (dF[3 * c + a1] * lamh[a2] - dF[3 * c + a2] * lamh[a1]); }
@@ -282,177 +204,120 @@ CMPC_FN double hess_dz_entry(const Config& cfg, const double* rtab, const double
     const double* dc = dzk + NS + 6 + 12 * c + a;
     const double sum = dc[0] + dc[3] + dc[6] + dc[9];
     double r = 2.0 * cfg.w_sym * (own + (NJ * a4 * a4 - 2.0 * a4) * sum) + dw * own;
-    if (k > 0) r += 2.0 * cfg.w_rate[a] * (own - rdz[kr(k - 1) * ZS + v]);
-    if (k + 1 < N) r += 2.0 * cfg.w_rate[a] * (own - rdz[kr(k + 1) * ZS + v]);
-    const double* lamh = rlam + kr(k + 1) * ES + 6;
+    if (k > 0) r += 2.0 * cfg.w_rate[a] * (own - w.dz[(k - 1) * ZS + v]);
+    if (k + 1 < N) r += 2.0 * cfg.w_rate[a] * (own - w.dz[(k + 1) * ZS + v]);
+    const double* lamh = w.lam + (k + 1) * ES + 6;
     const double e1 = dzk[a1] - dzk[9 + 3 * c + a1], e2 = dzk[a2] - dzk[9 + 3 * c + a2];
     r += cfg.dT * t[T_EN + c] * (lamh[a1] * e2 - lamh[a2] * e1);
     return r;
 }
 
 // ------------------------------------------------------------------------------------------------ evaluation of a point
-// stage data, equality residuals, path row values, objective, theta (l1 infeasibility) and the barrier function at the
-// current point (TRIAL = false) or at the trial point (z + alpha dz, sl + alpha dsl) of the line search, which is formed on
-// the fly from the staged z, dz and written to zt / slt (TRIAL = true).  Also the values of the off-diagonal non-zeros of A at
-// the point (aw: needed by jty_entry and by the adjoint recursion).
-template <bool TRIAL>
-struct PointZ {
-    const double* z; const double* dz; double alpha;
-    CMPC_HD double operator()(int k, int i) const
-    {
-        const int o = kr(k) * ZS + i;
-        return TRIAL ? fma(alpha, dz[o], z[o]) : z[o];
-    }
-};
-template <int NT, int G, bool TRIAL, class Cta>
-CMPC_FN void eval_point(Team T, Cta& cta, const Config& cfg, ISmem& sm, double alpha, double mu)
+// stage data, equality residuals, path row values, objective, theta (l1 infeasibility) and the barrier function at (zsrc, slsrc)
+template <int NT, int G, class Cta>
+CMPC_FN void eval_point(Team T, Cta& cta, const Config& cfg, ISmem& sm, const double* zsrc, const double* slsrc, double mu)
 {
-    cta_align<G>();
+    cta_align<G>(T);
     const WorkS& w = sm.w;
     const int N = cfg.N;
     const double dT = cfg.dT;
-    constexpr int R_TAB = 0, R_Z = R_TAB + 4 * TS, R_DZ = R_Z + 4 * ZS, R_BEQ = R_DZ + 4 * ZS, R_LO = R_BEQ + 4 * ES, R_UP = R_LO + 4 * PS,
-                  R_SL = R_UP + 4 * PS, R_DSL = R_SL + 4 * PS, R_SD = R_DSL + 4 * PS, R_END = R_SD + 4 * SD_STRIDE;
-    static_assert(R_END <= RING_CAP, "ring overflow");
     CMPC_LANES
-        if (lane == 0) {
-            int s = 0;
-            ring_seg(sm, s++, w.tab, R_TAB, TS, TS / 2, N + 1);
-            ring_seg(sm, s++, w.z, R_Z, ZS, ZS / 2, N + 1);
-            ring_seg(sm, s++, w.lo, R_LO, PS, PS / 2, N);
-            ring_seg(sm, s++, w.up, R_UP, PS, PS / 2, N);
-            ring_seg(sm, s++, w.sl, R_SL, PS, PS / 2, N);
-            ring_seg(sm, s++, w.beq, R_BEQ, ES, ES / 2, N + 1);
-            if (TRIAL) {
-                ring_seg(sm, s++, w.dz, R_DZ, ZS, ZS / 2, N + 1);
-                ring_seg(sm, s++, w.dsl, R_DSL, PS, PS / 2, N);
+        CMPC_ROLES(32) CMPC_KNOTS(0, N - 1) {
+            const double* t = w.tab + k * TS;
+            const double* zk = zsrc + k * ZS;
+            double* d = w.sd + k * SD_STRIDE;
+            if (r < 24) {
+                const int c = r >= 12 ? 1 : 0, a = (r - 12 * c) % 3;
+                d[SD_RHO + r] = t[T_RR + r] + zk[9 + 3 * c + a] - zk[a];
+            } else if (r < 30) {
+                const int q = r - 24, c = q / 3, a = q - 3 * c;
+                const double* fc = zk + NS + 6 + 12 * c + a;
+                d[SD_FC + q] = fc[0] + fc[3] + fc[6] + fc[9];
+            } else {
+                d[SD_EN + r - 30] = t[T_EN + r - 30];
+                d[SD_VM + r - 30] = t[T_VM + r - 30];
             }
-            sm.nseg = s;
         }
-    CMPC_LANES_END_NOSYNC
+    CMPC_LANES_END
     double acc[3] = {0.0, 0.0, 0.0};  // f, theta, barrier terms
-    CMPC_RING_PASS_BEGIN(0, N)
-            const double* rtab = ring + R_TAB;
-            const PointZ<TRIAL> Z{ring + R_Z, ring + R_DZ, alpha};
-            const double* t = rtab + kr(k) * TS;
-            double* rsd = ring + R_SD;
-            for (int it = lane; it < 96; it += NT) {
-                if (it < 35) {
-                    if (k < N) {
-                        double* d = rsd + kr(k) * SD_STRIDE;
-                        double* dg = w.sd + k * SD_STRIDE;
-                        if (it < 24) {
-                            const int c = it >= 12 ? 1 : 0, a = (it - 12 * c) % 3;
-                            const double v = t[T_RR + it] + Z(k, 9 + 3 * c + a) - Z(k, a);
-                            d[SD_RHO + it] = v; dg[SD_RHO + it] = v;
-                        } else if (it < 30) {
-                            const int q = it - 24, c = q / 3, a = q - 3 * c, b = NS + 6 + 12 * c + a;
-                            const double v = Z(k, b) + Z(k, b + 3) + Z(k, b + 6) + Z(k, b + 9);
-                            d[SD_FC + q] = v; dg[SD_FC + q] = v;
-                        } else if (it < 32) {
-                            const double en = t[T_EN + it - 30], vm = t[T_VM + it - 30];
-                            d[SD_EN + it - 30] = en; d[SD_VM + it - 30] = vm; dg[SD_EN + it - 30] = en; dg[SD_VM + it - 30] = vm;
-                        } else {
-                            const int a = it - 32, b0 = NS + 6 + a, b1 = NS + 18 + a;
-                            const double f0 = Z(k, b0) + Z(k, b0 + 3) + Z(k, b0 + 6) + Z(k, b0 + 9);
-                            const double f1 = Z(k, b1) + Z(k, b1 + 3) + Z(k, b1 + 6) + Z(k, b1 + 9);
-                            const double v = t[T_EN] * f0 + t[T_EN + 1] * f1;
-                            d[SD_FALL + a] = v; dg[SD_FALL + a] = v;
-                        }
-                    }
-                } else if (it < 50) {
-                    // equality row block k: the rows that define s_k (k = 0: initial condition, k >= 1: dynamics of knot k - 1)
-                    const int r = it - 35;
-                    const double zr = Z(k, r);
-                    double c;
-                    if (k == 0) c = zr;
-                    else {
-                        const double* tp = rtab + kr(k - 1) * TS;
-                        const double* d = rsd + kr(k - 1) * SD_STRIDE;
-                        c = zr - Z(k - 1, r);
-                        if (r < 3) c -= dT * Z(k - 1, 3 + r);
-                        else if (r < 6) {
-                            const int a = r - 3;
-                            c -= dT * ((a == 2 ? GRAV_Z : 0.0) + tp[T_EXTF + a] + tp[T_EN] * d[SD_FC + a] + tp[T_EN + 1] * d[SD_FC + 3 + a]);
-                        } else if (r < 9) {
-                            const int a = r - 6, a1 = (a + 1) % 3, a2 = (a + 2) % 3;
-                            double tq = tp[T_EXTT + a];
-                            for (int cc = 0; cc < NC; ++cc) {
-                                double s = 0.0;
-                                for (int j = 0; j < NJ; ++j) {
-                                    const double* rho = d + SD_RHO + 3 * (4 * cc + j);
-                                    const int fo = NS + 6 + 12 * cc + 3 * j;
-                                    s += rho[a1] * Z(k - 1, fo + a2) - rho[a2] * Z(k - 1, fo + a1);
-                                }
-                                tq += tp[T_EN + cc] * s;
+    CMPC_LANES
+        CMPC_ROLES(63) CMPC_KNOTS(0, N) {
+            const double* t = w.tab + k * TS;
+            const double* zk = zsrc + k * ZS;
+            if (r < NS) {
+                // equality row block k: the rows that define s_k (k = 0: initial condition, k >= 1: dynamics of knot k - 1)
+                double c;
+                if (k == 0) c = zk[r];
+                else {
+                    const double* zp = zsrc + (k - 1) * ZS;
+                    const double* tp = w.tab + (k - 1) * TS;
+                    const double* d = w.sd + (k - 1) * SD_STRIDE;
+                    c = zk[r] - zp[r];
+                    if (r < 3) c -= dT * zp[3 + r];
+                    else if (r < 6) {
+                        const int a = r - 3;
+                        c -= dT * ((a == 2 ? GRAV_Z : 0.0) + tp[T_EXTF + a] + tp[T_EN] * d[SD_FC + a] + tp[T_EN + 1] * d[SD_FC + 3 + a]);
+                    } else if (r < 9) {
+                        const int a = r - 6, a1 = (a + 1) % 3, a2 = (a + 2) % 3;
+                        double tq = tp[T_EXTT + a];
+                        for (int cc = 0; cc < NC; ++cc) {
+                            double s = 0.0;
+                            for (int j = 0; j < NJ; ++j) {
+                                const double* rho = d + SD_RHO + 3 * (4 * cc + j);
+                                const double* fo = zp + NS + 6 + 12 * cc + 3 * j;
+                                s += rho[a1] * fo[a2] - rho[a2] * fo[a1];
                             }
-                            c -= dT * tq;
-                        } else {
-                            const int cc = (r - 9) / 3;
-                            c -= tp[T_OMD + cc] * Z(k - 1, NS + r - 9);
+                            tq += tp[T_EN + cc] * s;
                         }
-                        // values of the off-diagonal non-zeros of column r of A at knot k - 1 (complete since the last stage)
-                        double v2[2];
-                        acol_vals(r, d, dT, v2);
-                        w.aw[(k - 1) * AWS + 2 * r] = v2[0]; w.aw[(k - 1) * AWS + 2 * r + 1] = v2[1];
-                    }
-                    c -= ring[R_BEQ + kr(k) * ES + r];
-                    w.ceq[k * ES + r] = c;
-                    acc[1] += fabs(c);
-                    // stage cost of s_k[r]
-                    if (r < 2) { const double e = zr - t[T_CREF + r]; acc[0] += cfg.w_com[r] * e * e; }
-                    else if (r == 2) { const double e = zr - t[T_CREF + 2]; acc[0] += t[T_OM2] * e * e; }
-                    else if (r >= 6 && r < 9) { const double e = zr - t[T_HREF + r - 6]; acc[0] += cfg.w_h * e * e; }
-                    else if (r >= 9) { const double e = zr - t[T_NOM + r - 9]; acc[0] += cfg.w_pos * e * e; }
-                } else if (it < 88) {
-                    if (k < N) {
-                        const int l = it - 50, pr = k * PS + l, ro = kr(k) * PS + l;
-                        double g;
-                        if (l < 32) {
-                            const int c = l >> 4, j = (l >> 2) & 3, r = l & 3, f = NS + 6 + 12 * c + 3 * j;
-                            const double* ar = t + T_AR + 12 * c + 3 * r;
-                            g = ar[0] * Z(k, f) + ar[1] * Z(k, f + 1) + ar[2] * Z(k, f + 2);
-                        } else {
-                            const int q = l - 32, c = q / 3, qq = q - 3 * c;
-                            const double* rc = t + T_R + 9 * c + 3 * qq;  // column qq of R_c
-                            const double* nom = t + T_NOM1 + 3 * c;
-                            g = 0.0;
-                            for (int a = 0; a < 3; ++a) g += rc[a] * (Z(k + 1, 9 + 3 * c + a) - nom[a]);
-                        }
-                        w.gp[pr] = g;
-                        const double sl = ring[R_LO + ro], su = ring[R_UP + ro];
-                        const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
-                        const double s = TRIAL ? fma(alpha, ring[R_DSL + ro], ring[R_SL + ro]) : ring[R_SL + ro];
-                        if (TRIAL) w.slt[pr] = s;
-                        if (hl || hu) {
-                            if (sl == su) acc[1] += fabs(g - sl);
-                            else {
-                                acc[1] += fabs(g - s);
-                                if (hl) acc[2] -= mu * log(s - sl);
-                                if (hu) acc[2] -= mu * log(su - s);
-                                if (hl && !hu) acc[2] += KAPPA_D * mu * (s - sl);
-                                if (hu && !hl) acc[2] += KAPPA_D * mu * (su - s);
-                            }
-                        }
-                    }
-                } else if (it < 94) {
-                    if (k < N) {
-                        // force cost of (contact c, axis a): symmetry + rate of change
-                        const int q = it - 88, c = q / 3, a = q - 3 * c, b = NS + 6 + 12 * c + a;
-                        const double en = t[T_EN + c];
-                        const double f0 = Z(k, b), f1 = Z(k, b + 3), f2 = Z(k, b + 6), f3 = Z(k, b + 9);
-                        const double mean = en / NJ * (f0 + f1 + f2 + f3);
-                        for (int j = 0; j < NJ; ++j) {
-                            const double fj = j == 0 ? f0 : j == 1 ? f1 : j == 2 ? f2 : f3;
-                            const double dd = fj - mean;
-                            acc[0] += cfg.w_sym * dd * dd;
-                            if (k + 1 < N) { const double dn = Z(k + 1, b + 3 * j) - fj; acc[0] += cfg.w_rate[a] * dn * dn; }
-                        }
+                        c -= dT * tq;
+                    } else {
+                        const int cc = (r - 9) / 3;
+                        c -= tp[T_OMD + cc] * zp[NS + r - 9];
                     }
                 }
-                if (TRIAL && it < ZS) w.zt[k * ZS + it] = Z(k, it);
+                c -= w.beq[k * ES + r];
+                w.ceq[k * ES + r] = c;
+                acc[1] += fabs(c);
+                // stage cost of s_k[r]
+                if (r < 2) { const double e = zk[r] - t[T_CREF + r]; acc[0] += cfg.w_com[r] * e * e; }
+                else if (r == 2) { const double e = zk[2] - t[T_CREF + 2]; acc[0] += t[T_OM2] * e * e; }
+                else if (r >= 6 && r < 9) { const double e = zk[r] - t[T_HREF + r - 6]; acc[0] += cfg.w_h * e * e; }
+                else if (r >= 9) { const double e = zk[r] - t[T_NOM + r - 9]; acc[0] += cfg.w_pos * e * e; }
+            } else if (k < N && r >= 16 && r < 16 + 38) {
+                const int l = r - 16, pr = k * PS + l;
+                const double g = path_dot(t, zk, zsrc + (k + 1) * ZS, l, 1);
+                w.gp[pr] = g;
+                const double sl = w.lo[pr], su = w.up[pr];
+                const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
+                if (hl || hu) {
+                    if (sl == su) acc[1] += fabs(g - sl);
+                    else {
+                        const double s = slsrc[pr];
+                        acc[1] += fabs(g - s);
+                        if (hl) acc[2] -= mu * log(s - sl);
+                        if (hu) acc[2] -= mu * log(su - s);
+                        if (hl && !hu) acc[2] += KAPPA_D * mu * (s - sl);
+                        if (hu && !hl) acc[2] += KAPPA_D * mu * (su - s);
+                    }
+                }
+            } else if (k < N && r >= 54 && r < 60) {
+                // force cost of (contact c, axis a): symmetry + rate of change
+                const int q = r - 54, c = q / 3, a = q - 3 * c;
+                const double en = t[T_EN + c];
+                const double* fc = zk + NS + 6 + 12 * c + a;
+                const double mean = en / NJ * (fc[0] + fc[3] + fc[6] + fc[9]);
+                for (int j = 0; j < NJ; ++j) {
+                    const double dd = fc[3 * j] - mean;
+                    acc[0] += cfg.w_sym * dd * dd;
+                    if (k + 1 < N) { const double dn = fc[3 * j + ZS] - fc[3 * j]; acc[0] += cfg.w_rate[a] * dn * dn; }
+                }
+            } else if (k < N && r >= 60 && r < 63) {
+                const int a = r - 60;
+                const double* d = w.sd + k * SD_STRIDE;
+                w.sd[k * SD_STRIDE + SD_FALL + a] = t[T_EN] * d[SD_FC + a] + t[T_EN + 1] * d[SD_FC + 3 + a];
             }
-    CMPC_RING_PASS_END
+        }
+    CMPC_LANES_END_NOSYNC
     cta.template reduce3<0, 0, 3>(acc, acc, acc);
     CMPC_LANES
         if (lane == 0) { sm.es.f = acc[0]; sm.es.theta = acc[1]; sm.es.phi = acc[0] + acc[2]; }
@@ -473,65 +338,54 @@ CMPC_HD double kkt_E(const KktStats& s, double mu, double* compl_out)
 template <int NT, int G, class Cta>
 CMPC_FN void kkt_pass(Team T, Cta& cta, const Config& cfg, ISmem& sm)
 {
-    cta_align<G>();
+    cta_align<G>(T);
     const WorkS& w = sm.w;
     const int N = cfg.N;
-    constexpr int R_TAB = 0, R_Z = R_TAB + 4 * TS, R_LAM = R_Z + 4 * ZS, R_CEQ = R_LAM + 4 * ES, R_SD = R_CEQ + 4 * ES,
-                  R_AW = R_SD + 4 * SD_STRIDE, R_YP = R_AW + 4 * AWS, R_LO = R_YP + 4 * PS, R_UP = R_LO + 4 * PS, R_GP = R_UP + 4 * PS,
-                  R_SL = R_GP + 4 * PS, R_ZL = R_SL + 4 * PS, R_ZU = R_ZL + 4 * PS, R_END = R_ZU + 4 * PS;
-    static_assert(R_END <= RING_CAP, "ring overflow");
+    // the values of the off-diagonal non-zeros of A at the iterate (needed by jty_entry and by the adjoint recursion)
     CMPC_LANES
-        if (lane == 0) {
-            int s = 0;
-            ring_seg(sm, s++, w.tab, R_TAB, TS, TS / 2, N + 1);
-            ring_seg(sm, s++, w.z, R_Z, ZS, ZS / 2, N + 1);
-            ring_seg(sm, s++, w.yp, R_YP, PS, PS / 2, N);
-            ring_seg(sm, s++, w.lam, R_LAM, ES, ES / 2, N + 1);
-            ring_seg(sm, s++, w.sd, R_SD, SD_STRIDE, SD_STRIDE / 2, N);
-            ring_seg(sm, s++, w.aw, R_AW, AWS, AWS / 2, N);
-            ring_seg(sm, s++, w.ceq, R_CEQ, ES, ES / 2, N + 1);
-            ring_seg(sm, s++, w.lo, R_LO, PS, PS / 2, N);
-            ring_seg(sm, s++, w.up, R_UP, PS, PS / 2, N);
-            ring_seg(sm, s++, w.gp, R_GP, PS, PS / 2, N);
-            ring_seg(sm, s++, w.sl, R_SL, PS, PS / 2, N);
-            ring_seg(sm, s++, w.zl, R_ZL, PS, PS / 2, N);
-            ring_seg(sm, s++, w.zu, R_ZU, PS, PS / 2, N);
-            sm.nseg = s;
+        CMPC_ROLES(NS) CMPC_KNOTS(0, N - 1) {
+            const int i = r;
+            {
+                double v2[2];
+                acol_vals(i, w.sd + k * SD_STRIDE, cfg.dT, v2);
+                w.aw[k * AWS + 2 * i] = v2[0]; w.aw[k * AWS + 2 * i + 1] = v2[1];
+            }
         }
-    CMPC_LANES_END_NOSYNC
+    CMPC_LANES_END
     double vmax[3] = {0.0, 0.0, -HUGE_VAL};   // dual, viol, pmax
     double vmin[1] = {HUGE_VAL};              // pmin
     double vsum[4] = {0.0, 0.0, 0.0, 0.0};    // |y|, z, bounds, rows
-    CMPC_RING_PASS_BEGIN(0, N)
-            for (int it = lane; it < 96; it += NT) {
-                if (it < NS + NU) {
-                    if (k == N && it >= NS) continue;
-                    const double g = grad_entry(cfg, ring + R_TAB, ring + R_Z, k, it);
-                    w.gr[k * ZS + it] = g;
-                    vmax[0] = fmax(vmax[0], fabs(g + jty_entry(cfg, ring + R_TAB, ring + R_SD, ring + R_AW, ring + R_LAM, ring + R_YP, k, it)));
-                    if (it < NS) {  // the equality row that defines s_k[it]
-                        vmax[1] = fmax(vmax[1], fabs(ring[R_CEQ + kr(k) * ES + it]));
-                        vsum[0] += fabs(ring[R_LAM + kr(k) * ES + it]);
-                        vsum[3] += 1.0;
-                    }
-                } else if (it >= 48 && it < 48 + 38 && k < N) {
-                    const int ro = kr(k) * PS + it - 48;
-                    const double sl = ring[R_LO + ro], su = ring[R_UP + ro];
-                    const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
-                    if (!hl && !hu) continue;
-                    const double y = ring[R_YP + ro], g = ring[R_GP + ro];
-                    vsum[0] += fabs(y);
+    CMPC_LANES
+        CMPC_ROLES(48 + 38) CMPC_KNOTS(0, N) {
+            if (r < NS + NU) {
+                if (k == N && r >= NS) continue;
+                const double g = grad_entry(cfg, w, w.z, k, r);
+                w.gr[k * ZS + r] = g;
+                vmax[0] = fmax(vmax[0], fabs(g + jty_entry(cfg, w, w.lam, w.yp, k, r)));
+                if (r < NS) {  // the equality row that defines s_k[r]
+                    const int e = k * ES + r;
+                    vmax[1] = fmax(vmax[1], fabs(w.ceq[e]));
+                    vsum[0] += fabs(w.lam[e]);
                     vsum[3] += 1.0;
-                    if (sl == su) { vmax[1] = fmax(vmax[1], fabs(g - sl)); continue; }
-                    const double s = ring[R_SL + ro];
-                    vmax[1] = fmax(vmax[1], fabs(g - s));
-                    double dsl = -y;
-                    if (hl) { const double z = ring[R_ZL + ro], pd = (s - sl) * z; dsl -= z; vsum[1] += z; vsum[2] += 1.0; vmax[2] = fmax(vmax[2], pd); vmin[0] = fmin(vmin[0], pd); }
-                    if (hu) { const double z = ring[R_ZU + ro], pd = (su - s) * z; dsl += z; vsum[1] += z; vsum[2] += 1.0; vmax[2] = fmax(vmax[2], pd); vmin[0] = fmin(vmin[0], pd); }
-                    vmax[0] = fmax(vmax[0], fabs(dsl));
                 }
+            } else if (k < N && r >= 48) {
+                const int pr = k * PS + r - 48;
+                const double sl = w.lo[pr], su = w.up[pr];
+                const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
+                if (!hl && !hu) continue;
+                const double y = w.yp[pr], g = w.gp[pr];
+                vsum[0] += fabs(y);
+                vsum[3] += 1.0;
+                if (sl == su) { vmax[1] = fmax(vmax[1], fabs(g - sl)); continue; }
+                const double s = w.sl[pr];
+                vmax[1] = fmax(vmax[1], fabs(g - s));
+                double dsl = -y;
+                if (hl) { const double z = w.zl[pr], pd = (s - sl) * z; dsl -= z; vsum[1] += z; vsum[2] += 1.0; vmax[2] = fmax(vmax[2], pd); vmin[0] = fmin(vmin[0], pd); }
+                if (hu) { const double z = w.zu[pr], pd = (su - s) * z; dsl += z; vsum[1] += z; vsum[2] += 1.0; vmax[2] = fmax(vmax[2], pd); vmin[0] = fmin(vmin[0], pd); }
+                vmax[0] = fmax(vmax[0], fabs(dsl));
             }
-    CMPC_RING_PASS_END
+        }
+    CMPC_LANES_END_NOSYNC
     cta.template reduce3<3, 1, 4>(vmax, vmin, vsum);
     CMPC_LANES
         if (lane == 0) {
@@ -542,249 +396,164 @@ CMPC_FN void kkt_pass(Team T, Cta& cta, const Config& cfg, ISmem& sm)
     CMPC_LANES_END
 }
 
-// Sigma and the barrier gradient terms of the path rows, then the small blocks of the Riccati sweep for every knot.
-// Stage k (-1 .. N) computes sigma / tt of knot k + 1 and the small blocks of knot k (which need sigma / tt of knots k - 1, k).
+// Sigma and the barrier gradient terms of the path rows, then the small blocks of the Riccati sweep for every knot
 template <int NT, int G>
-CMPC_FN void barrier_pass(Team T, const Config& cfg, ISmem& sm, double mu, double dw, double dc)
+CMPC_FN void barrier_pass(Team T, const Config& cfg, const WorkS& w, double mu, double dw, double dc)
 {
-    cta_align<G>();
-    const WorkS& w = sm.w;
+    cta_align<G>(T);
     const int N = cfg.N;
-    constexpr int R_TAB = 0, R_GR = R_TAB + 4 * TS, R_LAM = R_GR + 4 * ZS, R_CEQ = R_LAM + 4 * ES, R_YP = R_CEQ + 4 * ES,
-                  R_LO = R_YP + 4 * PS, R_UP = R_LO + 4 * PS, R_GP = R_UP + 4 * PS, R_SL = R_GP + 4 * PS, R_ZL = R_SL + 4 * PS,
-                  R_ZU = R_ZL + 4 * PS, R_SIG = R_ZU + 4 * PS, R_TT = R_SIG + 4 * PS, R_END = R_TT + 4 * PS;
-    static_assert(R_END <= RING_CAP, "ring overflow");
     CMPC_LANES
-        if (lane == 0) {
-            int s = 0;
-            ring_seg(sm, s++, w.tab, R_TAB, TS, TS / 2, N + 1);
-            ring_seg(sm, s++, w.gr, R_GR, ZS, ZS / 2, N + 1);
-            ring_seg(sm, s++, w.yp, R_YP, PS, PS / 2, N);
-            ring_seg(sm, s++, w.lam, R_LAM, ES, ES / 2, N + 1);
-            ring_seg(sm, s++, w.ceq, R_CEQ, ES, ES / 2, N + 1);
-            ring_seg(sm, s++, w.lo, R_LO, PS, PS / 2, N);
-            ring_seg(sm, s++, w.up, R_UP, PS, PS / 2, N);
-            ring_seg(sm, s++, w.gp, R_GP, PS, PS / 2, N);
-            ring_seg(sm, s++, w.sl, R_SL, PS, PS / 2, N);
-            ring_seg(sm, s++, w.zl, R_ZL, PS, PS / 2, N);
-            ring_seg(sm, s++, w.zu, R_ZU, PS, PS / 2, N);
-            sm.nseg = s;
-        }
-    CMPC_LANES_END_NOSYNC
-    CMPC_RING_PASS_BEGIN(-1, N)
-            for (int it = lane; it < 40 + 123; it += NT) {
-                if (it < 40) {
-                    // sigma / tt of path row `it` of knot k + 1 (the two pad rows of every knot have no bounds: 0)
-                    const int k1 = k + 1;
-                    if (k1 >= N) continue;
-                    const int ro = kr(k1) * PS + it;
-                    const double sl = ring[R_LO + ro], su = ring[R_UP + ro];
-                    const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
-                    double sg = 0.0, t = 0.0;
-                    if (hl || hu) {
-                        const double y = ring[R_YP + ro], g = ring[R_GP + ro];
-                        if (sl == su) { sg = 1.0 / dc; t = y + (g - sl) / dc; }
-                        else {
-                            const double s = ring[R_SL + ro];
-                            sg = dw;
-                            if (hl) { const double dd = s - sl; sg += ring[R_ZL + ro] / dd; t -= mu / dd; }
-                            if (hu) { const double dd = su - s; sg += ring[R_ZU + ro] / dd; t += mu / dd; }
-                            if (hl && !hu) t += KAPPA_D * mu;
-                            if (hu && !hl) t -= KAPPA_D * mu;
-                            t += sg * (g - s);
-                        }
+        {
+            const double* __restrict__ lo = w.lo; const double* __restrict__ up = w.up; const double* __restrict__ ypp = w.yp;
+            const double* __restrict__ gpp = w.gp; const double* __restrict__ slp = w.sl; const double* __restrict__ zlp = w.zl;
+            const double* __restrict__ zup = w.zu; double* __restrict__ sigp = w.sig; double* __restrict__ ttp = w.tt;
+            CMPC_UNROLL2
+            for (int pr = lane; pr < N * PS; pr += NT) {  // the two pad rows of every knot have no bounds: sig = tt = 0
+                const double sl = lo[pr], su = up[pr], y = ypp[pr], g = gpp[pr], s = slp[pr], zl = zlp[pr], zu = zup[pr];
+                const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
+                double sg = 0.0, t = 0.0;
+                if (hl || hu) {
+                    if (sl == su) { sg = 1.0 / dc; t = y + (g - sl) / dc; }
+                    else {
+                        sg = dw;
+                        if (hl) { const double dd = s - sl; sg += zl / dd; t -= mu / dd; }
+                        if (hu) { const double dd = su - s; sg += zu / dd; t += mu / dd; }
+                        if (hl && !hu) t += KAPPA_D * mu;
+                        if (hu && !hl) t -= KAPPA_D * mu;
+                        t += sg * (g - s);
                     }
-                    ring[R_SIG + ro] = sg; ring[R_TT + ro] = t;
-                    w.sig[k1 * PS + it] = sg; w.tt[k1 * PS + it] = t;
-                    continue;
                 }
-                if (k < 0) continue;
-                const int r = it - 40;
-                const double* t = ring + R_TAB + kr(k) * TS;
-                double val = 0.0;
-                if (r < 48) {  // friction barrier block of corner cj, packed entry e
-                    if (k < N) {
-                        const int cj = r / 6, e = r - 6 * cj, c = cj >> 2;
-                        const int a = e < 3 ? 0 : (e < 5 ? 1 : 2), b = e < 3 ? e : (e < 5 ? e - 2 : 2);
-                        const double* ar = t + T_AR + 12 * c;
-                        const double* sg = ring + R_SIG + kr(k) * PS + 4 * cj;
-                        for (int q = 0; q < NF; ++q) val += sg[q] * ar[3 * q + a] * ar[3 * q + b];
-                    }
-                } else if (r < 60) {  // step-box barrier block on pos_c of knot k (rows of knot k - 1)
-                    if (k > 0) {
-                        const int t2 = r - 48, c = t2 / 6, e = t2 - 6 * c;
-                        const int a = e < 3 ? 0 : (e < 5 ? 1 : 2), b = e < 3 ? e : (e < 5 ? e - 2 : 2);
-                        const double* R = ring + R_TAB + kr(k - 1) * TS + T_R + 9 * c;
-                        const double* sg = ring + R_SIG + kr(k - 1) * PS + 32 + 3 * c;
-                        for (int q = 0; q < 3; ++q) val += sg[q] * R[3 * q + a] * R[3 * q + b];
-                    }
-                } else if (r < 60 + NS) {
-                    const int i = r - 60;
-                    val = ring[R_GR + kr(k) * ZS + i];
-                    if (k > 0 && i >= 9) {
-                        const int c = (i - 9) / 3, a = (i - 9) % 3;
-                        const double* R = ring + R_TAB + kr(k - 1) * TS + T_R + 9 * c;
-                        const double* tb = ring + R_TT + kr(k - 1) * PS + 32 + 3 * c;
-                        for (int q = 0; q < 3; ++q) val += R[3 * q + a] * tb[q];
-                    }
-                } else if (r < 60 + NS + NU) {
-                    if (k < N) {
-                        const int u = r - 60 - NS;
-                        val = ring[R_GR + kr(k) * ZS + NS + u];
-                        if (u >= 6) {
-                            const int f = u - 6, c = f / 12, j = (f % 12) / 3, a = f % 3;
-                            const double* ar = t + T_AR + 12 * c + a;
-                            const double* tf = ring + R_TT + kr(k) * PS + 16 * c + 4 * j;
-                            for (int q = 0; q < NF; ++q) val += ar[3 * q] * tf[q];
-                        }
-                    }
-                } else if (r < 60 + NS + NU + NS) {
-                    if (k < N) val = -ring[R_CEQ + kr(k + 1) * ES + r - 60 - NS - NU];
-                } else {
-                    if (k < N) val = ring[R_LAM + kr(k + 1) * ES + 6 + r - 60 - NS - NU - NS];
-                }
-                w.small[(size_t)k * SMALL_STRIDE + r] = val;  // SmallBlk is laid out in item order
+                sigp[pr] = sg; ttp[pr] = t;
             }
-    CMPC_RING_PASS_END
+        }
+    CMPC_LANES_END
+    CMPC_LANES
+        CMPC_ROLES(123) CMPC_KNOTS(0, N) {
+            const double* t = w.tab + k * TS;
+            double val = 0.0;
+            if (r < 48) {  // friction barrier block of corner cj, packed entry e
+                if (k < N) {
+                    const int cj = r / 6, e = r - 6 * cj, c = cj >> 2;
+                    const int a = e < 3 ? 0 : (e < 5 ? 1 : 2), b = e < 3 ? e : (e < 5 ? e - 2 : 2);
+                    const double* ar = t + T_AR + 12 * c;
+                    const double* sg = w.sig + k * PS + 4 * cj;
+                    for (int q = 0; q < NF; ++q) val += sg[q] * ar[3 * q + a] * ar[3 * q + b];
+                }
+            } else if (r < 60) {  // step-box barrier block on pos_c of knot k (rows of knot k - 1)
+                if (k > 0) {
+                    const int t2 = r - 48, c = t2 / 6, e = t2 - 6 * c;
+                    const int a = e < 3 ? 0 : (e < 5 ? 1 : 2), b = e < 3 ? e : (e < 5 ? e - 2 : 2);
+                    const double* R = w.tab + (k - 1) * TS + T_R + 9 * c;
+                    const double* sg = w.sig + (k - 1) * PS + 32 + 3 * c;
+                    for (int q = 0; q < 3; ++q) val += sg[q] * R[3 * q + a] * R[3 * q + b];
+                }
+            } else if (r < 60 + NS) {
+                const int i = r - 60;
+                val = w.gr[k * ZS + i];
+                if (k > 0 && i >= 9) {
+                    const int c = (i - 9) / 3, a = (i - 9) % 3;
+                    const double* R = w.tab + (k - 1) * TS + T_R + 9 * c;
+                    const double* tb = w.tt + (k - 1) * PS + 32 + 3 * c;
+                    for (int q = 0; q < 3; ++q) val += R[3 * q + a] * tb[q];
+                }
+            } else if (r < 60 + NS + NU) {
+                if (k < N) {
+                    const int u = r - 60 - NS;
+                    val = w.gr[k * ZS + NS + u];
+                    if (u >= 6) {
+                        const int f = u - 6, c = f / 12, j = (f % 12) / 3, a = f % 3;
+                        const double* ar = t + T_AR + 12 * c + a;
+                        const double* tf = w.tt + k * PS + 16 * c + 4 * j;
+                        for (int q = 0; q < NF; ++q) val += ar[3 * q] * tf[q];
+                    }
+                }
+            } else if (r < 60 + NS + NU + NS) {
+                if (k < N) val = -w.ceq[(k + 1) * ES + r - 60 - NS - NU];
+            } else {
+                if (k < N) val = w.lam[(k + 1) * ES + 6 + r - 60 - NS - NU - NS];
+            }
+            w.small[(size_t)k * SMALL_STRIDE + r] = val;  // SmallBlk is laid out in item order
+        }
+    CMPC_LANES_END
 }
 
 // eliminated rows of the Newton system from dz (W-B eq. 13), then the multipliers of the equality rows by the adjoint
-// recursion  lambda+_k = A_k' lambda+_{k+1} - [grad f + W dz + sum_box a_i (y_i + dy_i)]_{s_k}  (exact for the given dz).
-// Stage k (-1 .. N) handles the path rows and the state rows of knot k and the total-force steps of knot k + 1.
+// recursion  lambda+_k = A_k' lambda+_{k+1} - [grad f + W dz + sum_box a_i (y_i + dy_i)]_{s_k}  (exact for the given dz)
 template <int NT, int G>
-CMPC_FN void recover_pass(Team T, const Config& cfg, ISmem& sm, double mu, double dw, double dc)
+CMPC_FN void recover_pass(Team T, const Config& cfg, const WorkS& w, double mu, double dw, double dc)
 {
-    cta_align<G>();
-    const WorkS& w = sm.w;
+    cta_align<G>(T);
     const int N = cfg.N;
-    constexpr int R_TAB = 0, R_DZ = R_TAB + 4 * TS, R_GR = R_DZ + 4 * ZS, R_LAM = R_GR + 4 * ZS, R_YP = R_LAM + 4 * ES,
-                  R_LO = R_YP + 4 * PS, R_UP = R_LO + 4 * PS, R_GP = R_UP + 4 * PS, R_SL = R_GP + 4 * PS, R_ZL = R_SL + 4 * PS,
-                  R_ZU = R_ZL + 4 * PS, R_SIG = R_ZU + 4 * PS, R_YPN = R_SIG + 4 * PS, R_DFC = R_YPN + 4 * PS, R_END = R_DFC + 4 * 8;
-    static_assert(R_END <= RING_CAP, "ring overflow");
     CMPC_LANES
-        if (lane == 0) {
-            int s = 0;
-            ring_seg(sm, s++, w.tab, R_TAB, TS, TS / 2, N + 1);
-            ring_seg(sm, s++, w.dz, R_DZ, ZS, ZS / 2, N + 1);
-            ring_seg(sm, s++, w.gr, R_GR, ZS, ZS / 2, N + 1);
-            ring_seg(sm, s++, w.yp, R_YP, PS, PS / 2, N);
-            ring_seg(sm, s++, w.lam, R_LAM, ES, ES / 2, N + 1);
-            ring_seg(sm, s++, w.sig, R_SIG, PS, PS / 2, N);
-            ring_seg(sm, s++, w.lo, R_LO, PS, PS / 2, N);
-            ring_seg(sm, s++, w.up, R_UP, PS, PS / 2, N);
-            ring_seg(sm, s++, w.gp, R_GP, PS, PS / 2, N);
-            ring_seg(sm, s++, w.sl, R_SL, PS, PS / 2, N);
-            ring_seg(sm, s++, w.zl, R_ZL, PS, PS / 2, N);
-            ring_seg(sm, s++, w.zu, R_ZU, PS, PS / 2, N);
-            sm.nseg = s;
-        }
-    CMPC_LANES_END_NOSYNC
-    CMPC_RING_PASS_BEGIN(-1, N)
-            for (int it = lane; it < 64; it += NT) {
-                if (it < 40) {
-                    if (k < 0 || k >= N) continue;
-                    const int pr = k * PS + it, ro = kr(k) * PS + it;
-                    double ds = 0.0, dzl = 0.0, dzu = 0.0, dy = 0.0, y = 0.0;
-                    if (it < 38) {
-                        const double sl = ring[R_LO + ro], su = ring[R_UP + ro];
-                        const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
-                        y = ring[R_YP + ro];
-                        if (hl || hu) {
-                            const double jd = path_dot(ring + R_TAB + kr(k) * TS, ring + R_DZ + kr(k) * ZS, ring + R_DZ + kr(k + 1) * ZS, it);
-                            const double gp = ring[R_GP + ro];
-                            if (sl == su) dy = (jd + (gp - sl)) / dc;
-                            else {
-                                const double s = ring[R_SL + ro];
-                                ds = jd + (gp - s);  // (g - s) first: jd can be below ulp(g)
-                                double rs = -y;
-                                if (hl) { const double dd = s - sl, zl = ring[R_ZL + ro]; rs -= mu / dd; dzl = mu / dd - zl - zl / dd * ds; }
-                                if (hu) { const double dd = su - s, zu = ring[R_ZU + ro]; rs += mu / dd; dzu = mu / dd - zu + zu / dd * ds; }
-                                if (hl && !hu) rs += KAPPA_D * mu;
-                                if (hu && !hl) rs -= KAPPA_D * mu;
-                                dy = ring[R_SIG + ro] * ds + rs;
-                            }
-                        }
+        CMPC_ROLES(46) CMPC_KNOTS(0, N - 1) {
+            const int l = r;
+            if (l < 38) {
+                const int pr = k * PS + l;
+                const double sl = w.lo[pr], su = w.up[pr];
+                const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
+                double ds = 0.0, dzl = 0.0, dzu = 0.0, dy = 0.0;
+                if (hl || hu) {
+                    const double jd = path_dot(w.tab + k * TS, w.dz + k * ZS, w.dz + (k + 1) * ZS, l, 0);
+                    if (sl == su) dy = (jd + (w.gp[pr] - sl)) / dc;
+                    else {
+                        const double s = w.sl[pr];
+                        ds = jd + (w.gp[pr] - s);  // (g - s) first: jd can be below ulp(g)
+                        double rs = -w.yp[pr];
+                        if (hl) { const double dd = s - sl; rs -= mu / dd; dzl = mu / dd - w.zl[pr] - w.zl[pr] / dd * ds; }
+                        if (hu) { const double dd = su - s; rs += mu / dd; dzu = mu / dd - w.zu[pr] + w.zu[pr] / dd * ds; }
+                        if (hl && !hu) rs += KAPPA_D * mu;
+                        if (hu && !hl) rs -= KAPPA_D * mu;
+                        dy = w.sig[pr] * ds + rs;
                     }
-                    w.dsl[pr] = ds; w.dzl[pr] = dzl; w.dzu[pr] = dzu; w.dyp[pr] = dy;
-                    w.ypn[pr] = y + dy; ring[R_YPN + ro] = y + dy;
-                } else if (it < 46) {  // step of the total force of contact c (for the bilinear hessian terms)
-                    const int k1 = k + 1;
-                    if (k1 >= N) continue;
-                    const int q = it - 40, c = q / 3, a = q - 3 * c;
-                    const double* dc4 = ring + R_DZ + kr(k1) * ZS + NS + 6 + 12 * c + a;
-                    const double v = dc4[0] + dc4[3] + dc4[6] + dc4[9];
-                    w.dfc[k1 * 8 + q] = v; ring[R_DFC + kr(k1) * 8 + q] = v;
-                } else if (it >= 48 && it < 48 + NS) {
-                    const int k0 = k, i = it - 48;
-                    if (k0 < 0) continue;
-                    double v = ring[R_GR + kr(k0) * ZS + i] + hess_dz_entry(cfg, ring + R_TAB, ring + R_DZ, ring + R_LAM, ring + R_DFC, dw, k0, i);
-                    if (k0 > 0 && i >= 9) {
-                        const int c = (i - 9) / 3, a = (i - 9) % 3;
-                        const double* R = ring + R_TAB + kr(k0 - 1) * TS + T_R + 9 * c;
-                        const double* yb = ring + R_YPN + kr(k0 - 1) * PS + 32 + 3 * c;
-                        v += R[a] * yb[0] + R[3 + a] * yb[1] + R[6 + a] * yb[2];
-                    }
-                    w.vco[k0 * ES + i] = v;
                 }
+                w.dsl[pr] = ds; w.dzl[pr] = dzl; w.dzu[pr] = dzu; w.dyp[pr] = dy;
+                w.ypn[pr] = w.yp[pr] + dy;
+            } else if (l >= 40 && l < 46) {  // step of the total force of contact c (for the bilinear hessian terms)
+                const int q = l - 40, c = q / 3, a = q - 3 * c;
+                const double* dc4 = w.dz + k * ZS + NS + 6 + 12 * c + a;
+                w.dfc[k * 8 + q] = dc4[0] + dc4[3] + dc4[6] + dc4[9];
             }
-    CMPC_RING_PASS_END
-    // adjoint recursion on warp 0: lane i holds lambda+_k[i]; A' couples it with two other lanes.  (vco, aw, lam) of the knots
-    // are prefetched into an 8-slot ring (64 doubles per knot, one 16-byte chunk per lane), 6 knots ahead
+        }
+    CMPC_LANES_END
+    CMPC_LANES
+        CMPC_ROLES(NS) CMPC_KNOTS(0, N) {
+            const int i = r;
+            double v = w.gr[k * ZS + i] + hess_dz_entry(cfg, w, dw, k, i);
+            if (k > 0 && i >= 9) {
+                const int c = (i - 9) / 3, a = (i - 9) % 3;
+                const double* R = w.tab + (k - 1) * TS + T_R + 9 * c;
+                const double* yb = w.ypn + (k - 1) * PS + 32 + 3 * c;
+                v += R[a] * yb[0] + R[3 + a] * yb[1] + R[6 + a] * yb[2];
+            }
+            w.vco[k * ES + i] = v;
+        }
+    CMPC_LANES_END
+    // adjoint recursion on warp 0: lane i holds lambda+_k[i]; A' couples it with two other lanes
     {
-        constexpr int AS = 8, AD = 6, ASTR = 64;  // slots, prefetch distance, doubles per slot: vco 16 | aw 32 | lam 16
-        double* const aring = sm.sw.P;
         LaneVal lamp;
         CMPC_WARP0
-            for (int q = 0; q < AD; ++q) {
-                const int kk = N - q;
-                if (kk >= 0) {
-                    double* dst = aring + (kk & (AS - 1)) * ASTR;
-                    if (lane < 8) async16(dst + 2 * lane, w.vco + kk * ES + 2 * lane);
-                    else if (lane < 24) { if (kk < N) async16(dst + 2 * lane, w.aw + kk * AWS + 2 * (lane - 8)); }
-                    else async16(dst + 2 * lane, w.lam + kk * ES + 2 * (lane - 24));
-                }
-                async_commit();
-            }
-            lamp.at(lane) = 0.0;
+            const double v = lane < NS ? -w.vco[N * ES + lane] : 0.0;
+            lamp.at(lane) = v;
+            if (lane < NS) { w.lamn[N * ES + lane] = v; w.dlam[N * ES + lane] = v - w.lam[N * ES + lane]; }
         CMPC_WARP0_END
         CMPC_IF_WARP0
         {
             CMPC_ROLLED
-            for (int k = N; k >= 0; --k) {
-                CMPC_WARP0
-                    async_wait<AD - 1>();
-                CMPC_WARP0_END
-                CMPC_SYNCWARP0
+            for (int k = N - 1; k >= 0; --k) {
                 lamp.snapshot();
                 CMPC_WARP0
-                    const double* slot = aring + (k & (AS - 1)) * ASTR;
                     int rr[2] = {0, 0};
                     if (lane < NS) acol_rows(lane, rr);
                     const double a0 = lamp.gather(lane, rr[0]), a1 = lamp.gather(lane, rr[1]);
                     if (lane < NS) {
-                        double v = -slot[lane];
-                        if (k < N) v += lamp.at(lane) + slot[16 + 2 * lane] * a0 + slot[16 + 2 * lane + 1] * a1;
+                        const double v = -w.vco[k * ES + lane] + lamp.at(lane) + w.aw[k * AWS + 2 * lane] * a0 + w.aw[k * AWS + 2 * lane + 1] * a1;
                         lamp.at(lane) = v;
                         w.lamn[k * ES + lane] = v;
-                        w.dlam[k * ES + lane] = v - slot[48 + lane];
+                        w.dlam[k * ES + lane] = v - w.lam[k * ES + lane];
                     }
-                CMPC_WARP0_END
-                CMPC_SYNCWARP0
-                CMPC_WARP0
-                    const int kk = k - AD;
-                    if (kk >= 0) {
-                        double* dst = aring + (kk & (AS - 1)) * ASTR;
-                        if (lane < 8) async16(dst + 2 * lane, w.vco + kk * ES + 2 * lane);
-                        else if (lane < 24) async16(dst + 2 * lane, w.aw + kk * AWS + 2 * (lane - 8));
-                        else async16(dst + 2 * lane, w.lam + kk * ES + 2 * (lane - 24));
-                    }
-                    async_commit();
                 CMPC_WARP0_END
             }
         }
-        CMPC_WARP0
-            async_wait<0>();
-        CMPC_WARP0_END
     }
     team_sync<NT, G>(T);
 }
@@ -794,75 +563,46 @@ CMPC_FN void recover_pass(Team T, const Config& cfg, ISmem& sm, double mu, doubl
 template <int NT, int G, class Cta>
 CMPC_FN void step_pass(Team T, Cta& cta, const Config& cfg, ISmem& sm, double mu, double dw, double tau)
 {
-    cta_align<G>();
+    cta_align<G>(T);
     const WorkS& w = sm.w;
     const int N = cfg.N;
-    constexpr int R_TAB = 0, R_DZ = R_TAB + 4 * TS, R_GR = R_DZ + 4 * ZS, R_LAM = R_GR + 4 * ZS, R_LAMN = R_LAM + 4 * ES,
-                  R_SD = R_LAMN + 4 * ES, R_AW = R_SD + 4 * SD_STRIDE, R_DFC = R_AW + 4 * AWS, R_YPN = R_DFC + 4 * 8, R_LO = R_YPN + 4 * PS,
-                  R_UP = R_LO + 4 * PS, R_SL = R_UP + 4 * PS, R_DSL = R_SL + 4 * PS, R_ZL = R_DSL + 4 * PS, R_ZU = R_ZL + 4 * PS,
-                  R_DZL = R_ZU + 4 * PS, R_DZU = R_DZL + 4 * PS, R_END = R_DZU + 4 * PS;
-    static_assert(R_END <= RING_CAP, "ring overflow");
-    CMPC_LANES
-        if (lane == 0) {
-            int s = 0;
-            ring_seg(sm, s++, w.tab, R_TAB, TS, TS / 2, N + 1);
-            ring_seg(sm, s++, w.dz, R_DZ, ZS, ZS / 2, N + 1);
-            ring_seg(sm, s++, w.gr, R_GR, ZS, ZS / 2, N + 1);
-            ring_seg(sm, s++, w.ypn, R_YPN, PS, PS / 2, N);
-            ring_seg(sm, s++, w.sd, R_SD, SD_STRIDE, SD_STRIDE / 2, N);
-            ring_seg(sm, s++, w.aw, R_AW, AWS, AWS / 2, N);
-            ring_seg(sm, s++, w.lam, R_LAM, ES, ES / 2, N + 1);
-            ring_seg(sm, s++, w.lamn, R_LAMN, ES, ES / 2, N + 1);
-            ring_seg(sm, s++, w.dfc, R_DFC, 8, 4, N);
-            ring_seg(sm, s++, w.lo, R_LO, PS, PS / 2, N);
-            ring_seg(sm, s++, w.up, R_UP, PS, PS / 2, N);
-            ring_seg(sm, s++, w.sl, R_SL, PS, PS / 2, N);
-            ring_seg(sm, s++, w.dsl, R_DSL, PS, PS / 2, N);
-            ring_seg(sm, s++, w.zl, R_ZL, PS, PS / 2, N);
-            ring_seg(sm, s++, w.zu, R_ZU, PS, PS / 2, N);
-            ring_seg(sm, s++, w.dzl, R_DZL, PS, PS / 2, N);
-            ring_seg(sm, s++, w.dzu, R_DZU, PS, PS / 2, N);
-            sm.nseg = s;
-        }
-    CMPC_LANES_END_NOSYNC
     double vmax[2] = {0.0, 0.0};    // rho, non-finite flag
     double vmin[2] = {1.0, 1.0};    // alpha_max (primal), alpha_z
     double vsum[1] = {0.0};         // dphi
-    CMPC_RING_PASS_BEGIN(0, N)
-            for (int it = lane; it < 96; it += NT) {
-                if (it < NS + NU) {
-                    if (k == N && it >= NS) continue;
-                    const double d = ring[R_DZ + kr(k) * ZS + it], g = ring[R_GR + kr(k) * ZS + it];
-                    double v = g + jty_entry(cfg, ring + R_TAB, ring + R_SD, ring + R_AW, ring + R_LAMN, ring + R_YPN, k, it)
-                               + hess_dz_entry(cfg, ring + R_TAB, ring + R_DZ, ring + R_LAM, ring + R_DFC, dw, k, it);
-                    if (it >= NS && it < NS + 6 && ring[R_TAB + kr(k) * TS + T_VM + (it - NS) / 3] != 0.0) v = 0.0;  // variable held fixed
-                    w.res[k * ZS + it] = v;
-                    vmax[0] = fmax(vmax[0], fabs(v));
-                    vsum[0] += g * d;
-                    if (!(fabs(d) < HUGE_VAL)) vmax[1] = 1.0;
-                } else if (it >= 48 && it < 48 + 38 && k < N) {
-                    const int ro = kr(k) * PS + it - 48;
-                    const double sl = ring[R_LO + ro], su = ring[R_UP + ro];
-                    const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
-                    if ((!hl && !hu) || sl == su) continue;
-                    const double s = ring[R_SL + ro], ds = ring[R_DSL + ro];
-                    if (hl) {
-                        const double dd = s - sl, dz = ring[R_DZL + ro];
-                        vsum[0] -= mu * ds / dd;
-                        if (ds < 0) vmin[0] = fmin(vmin[0], -tau * dd / ds);
-                        if (dz < 0) vmin[1] = fmin(vmin[1], -tau * ring[R_ZL + ro] / dz);
-                    }
-                    if (hu) {
-                        const double dd = su - s, dz = ring[R_DZU + ro];
-                        vsum[0] += mu * ds / dd;
-                        if (ds > 0) vmin[0] = fmin(vmin[0], tau * dd / ds);
-                        if (dz < 0) vmin[1] = fmin(vmin[1], -tau * ring[R_ZU + ro] / dz);
-                    }
-                    if (hl && !hu) vsum[0] += KAPPA_D * mu * ds;
-                    if (hu && !hl) vsum[0] -= KAPPA_D * mu * ds;
+    CMPC_LANES
+        CMPC_ROLES(48 + 38) CMPC_KNOTS(0, N) {
+            if (r < NS + NU) {
+                if (k == N && r >= NS) continue;
+                const double d = w.dz[k * ZS + r], g = w.gr[k * ZS + r];
+                double v = g + jty_entry(cfg, w, w.lamn, w.ypn, k, r) + hess_dz_entry(cfg, w, dw, k, r);
+                if (r >= NS && r < NS + 6 && w.tab[k * TS + T_VM + (r - NS) / 3] != 0.0) v = 0.0;  // variable held fixed
+                w.res[k * ZS + r] = v;
+                vmax[0] = fmax(vmax[0], fabs(v));
+                vsum[0] += g * d;
+                if (!(fabs(d) < HUGE_VAL)) vmax[1] = 1.0;
+            } else if (k < N && r >= 48) {
+                const int pr = k * PS + r - 48;
+                const double sl = w.lo[pr], su = w.up[pr];
+                const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
+                if ((!hl && !hu) || sl == su) continue;
+                const double s = w.sl[pr], ds = w.dsl[pr];
+                if (hl) {
+                    const double dd = s - sl, dz = w.dzl[pr];
+                    vsum[0] -= mu * ds / dd;
+                    if (ds < 0) vmin[0] = fmin(vmin[0], -tau * dd / ds);
+                    if (dz < 0) vmin[1] = fmin(vmin[1], -tau * w.zl[pr] / dz);
                 }
+                if (hu) {
+                    const double dd = su - s, dz = w.dzu[pr];
+                    vsum[0] += mu * ds / dd;
+                    if (ds > 0) vmin[0] = fmin(vmin[0], tau * dd / ds);
+                    if (dz < 0) vmin[1] = fmin(vmin[1], -tau * w.zu[pr] / dz);
+                }
+                if (hl && !hu) vsum[0] += KAPPA_D * mu * ds;
+                if (hu && !hl) vsum[0] -= KAPPA_D * mu * ds;
             }
-    CMPC_RING_PASS_END
+        }
+    CMPC_LANES_END_NOSYNC
     cta.template reduce3<2, 2, 1>(vmax, vmin, vsum);
     CMPC_LANES
         if (lane == 0) {
@@ -870,57 +610,6 @@ CMPC_FN void step_pass(Team T, Cta& cta, const Config& cfg, ISmem& sm, double mu
             s.rho = vmax[0]; s.bad = vmax[1]; s.amax = vmin[0]; s.az = vmin[1]; s.dphi = vsum[0];
         }
     CMPC_LANES_END
-}
-
-// multipliers of the accepted step: y += alpha dy, the bound multipliers with their own step size and IPOPT's kappa_sigma
-// safeguard (eq. 16), lambda += alpha dlambda
-template <int NT, int G>
-CMPC_FN void accept_pass(Team T, const Config& cfg, ISmem& sm, double mu, double alpha, double az)
-{
-    cta_align<G>();
-    const WorkS& w = sm.w;
-    const int N = cfg.N;
-    constexpr int R_LAM = 0, R_DLAM = R_LAM + 4 * ES, R_LO = R_DLAM + 4 * ES, R_UP = R_LO + 4 * PS, R_SL = R_UP + 4 * PS,
-                  R_YP = R_SL + 4 * PS, R_DYP = R_YP + 4 * PS, R_ZL = R_DYP + 4 * PS, R_ZU = R_ZL + 4 * PS, R_DZL = R_ZU + 4 * PS,
-                  R_DZU = R_DZL + 4 * PS, R_END = R_DZU + 4 * PS;
-    static_assert(R_END <= RING_CAP, "ring overflow");
-    CMPC_LANES
-        if (lane == 0) {
-            int s = 0;
-            ring_seg(sm, s++, w.lam, R_LAM, ES, ES / 2, N + 1);
-            ring_seg(sm, s++, w.dlam, R_DLAM, ES, ES / 2, N + 1);
-            ring_seg(sm, s++, w.lo, R_LO, PS, PS / 2, N);
-            ring_seg(sm, s++, w.up, R_UP, PS, PS / 2, N);
-            ring_seg(sm, s++, w.sl, R_SL, PS, PS / 2, N);
-            ring_seg(sm, s++, w.yp, R_YP, PS, PS / 2, N);
-            ring_seg(sm, s++, w.dyp, R_DYP, PS, PS / 2, N);
-            ring_seg(sm, s++, w.zl, R_ZL, PS, PS / 2, N);
-            ring_seg(sm, s++, w.zu, R_ZU, PS, PS / 2, N);
-            ring_seg(sm, s++, w.dzl, R_DZL, PS, PS / 2, N);
-            ring_seg(sm, s++, w.dzu, R_DZU, PS, PS / 2, N);
-            sm.nseg = s;
-        }
-    CMPC_LANES_END_NOSYNC
-    CMPC_RING_PASS_BEGIN(0, N)
-            for (int it = lane; it < 64; it += NT) {
-                if (it < 40) {
-                    if (k >= N) continue;
-                    const int pr = k * PS + it, ro = kr(k) * PS + it;
-                    const double sl = ring[R_LO + ro], su = ring[R_UP + ro], s = ring[R_SL + ro];
-                    const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
-                    const bool ineq = (hl || hu) && !(sl == su);
-                    w.yp[pr] = ring[R_YP + ro] + alpha * ring[R_DYP + ro];
-                    const double ddl = s - sl, ddu = su - s;
-                    const double zl1 = fmax(fmin(ring[R_ZL + ro] + az * ring[R_DZL + ro], KAPPA_SIGMA * mu / ddl), mu / (KAPPA_SIGMA * ddl));
-                    const double zu1 = fmax(fmin(ring[R_ZU + ro] + az * ring[R_DZU + ro], KAPPA_SIGMA * mu / ddu), mu / (KAPPA_SIGMA * ddu));
-                    if (ineq && hl) w.zl[pr] = zl1;
-                    if (ineq && hu) w.zu[pr] = zu1;
-                } else if (it >= 48) {
-                    const int i = it - 48;
-                    w.lam[k * ES + i] = ring[R_LAM + kr(k) * ES + i] + alpha * ring[R_DLAM + kr(k) * ES + i];
-                }
-            }
-    CMPC_RING_PASS_END
 }
 
 // ------------------------------------------------------------------------------------------------ the solver
@@ -979,11 +668,11 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
             if (inst >= batch) { alive = false; inst = -1; }
             else fresh = true;
         }
-        if (!vote_any<G>(alive)) break;
+        if (!vote_any<G>(T, alive)) break;
         int fin = -1;  // >= 0: the instance is finished with this status at the end of the round
 
         // ---- set-up of a fresh instance: table of constants, rows (classified, bounds relaxed), iterate; validation
-        if (vote_any<G>(fresh)) {
+        if (vote_any<G>(T, fresh)) {
             T.on = fresh;
             if (fresh) {
                 in.p = p_all + (size_t)inst * np; in.lbg = lbg_all + (size_t)inst * m; in.ubg = ubg_all + (size_t)inst * m;
@@ -1070,7 +759,7 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
             // initial point: slacks pushed inside their bounds (bound_push / bound_frac), bound multipliers 1
             T.on = fresh;
             if (fresh) { mu = cfg.mu_init; tau = fmax(TAU_MIN, 1.0 - mu); nfilt = 0; dw_last = 0.0; it = 0; }
-            eval_point<NT, G, false>(T, cta, cfg, ism, 0.0, mu);  // path row values (the slacks are not set yet)
+            eval_point<NT, G>(T, cta, cfg, ism, w.z, w.sl, mu);  // path row values (the slacks are not set yet)
     CMPC_LANES
         for (int it = lane; it < N * 64; it += NT) {
             const int k = it >> 6, l = it & 63;
@@ -1097,7 +786,7 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
             w.zl[pr] = zl; w.zu[pr] = zu;
         }
     CMPC_LANES_END
-            eval_point<NT, G, false>(T, cta, cfg, ism, 0.0, mu);
+            eval_point<NT, G>(T, cta, cfg, ism, w.z, w.sl, mu);
             if (fresh) {
                 f = ism.es.f; theta0 = ism.es.theta; phi0 = ism.es.phi;
                 theta_max = 1e4 * fmax(1.0, theta0); theta_min = 1e-4 * fmax(1.0, theta0);
@@ -1132,9 +821,9 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
         double dw = 0.0;
         int tries = 0;
         bool needf = act;
-        while (vote_any<G>(needf)) {
+        while (vote_any<G>(T, needf)) {
             T.on = needf;
-            barrier_pass<NT, G>(T, cfg, ism, mu, dw, dc);
+            barrier_pass<NT, G>(T, cfg, w, mu, dw, dc);
             CMPC_TOC(2)
             const int rc = riccati_backward<NT, G>(T, cfg, io, sm, dw);
             CMPC_TOC(3)
@@ -1151,7 +840,7 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
         T.on = act;
         riccati_forward<NT, G>(T, cfg, io, sm, false);
         CMPC_TOC(4)
-        recover_pass<NT, G>(T, cfg, ism, mu, dw, dc);
+        recover_pass<NT, G>(T, cfg, w, mu, dw, dc);
         CMPC_TOC(5)
         step_pass<NT, G>(T, cta, cfg, ism, mu, dw, tau);
         StepStats ss = ism.ss;
@@ -1161,12 +850,12 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
         int rf = 0;
         for (;;) {
             const bool needr = act && rf < MAX_REFINE && ss.rho > REFINE_TOL && !(ss.rho > 0.5 * rho_prev);
-            if (!vote_any<G>(needr)) break;
+            if (!vote_any<G>(T, needr)) break;
             T.on = needr;
             if (needr) rho_prev = ss.rho;
             refine_backward<NT, G>(T, cfg, io, sm);
             riccati_forward<NT, G>(T, cfg, io, sm, true);
-            recover_pass<NT, G>(T, cfg, ism, mu, dw, dc);
+            recover_pass<NT, G>(T, cfg, w, mu, dw, dc);
             step_pass<NT, G>(T, cta, cfg, ism, mu, dw, tau);
             if (needr) { ss = ism.ss; ++rf; }
         }
@@ -1177,9 +866,9 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
         double theta = theta0, phi = phi0;
         {
             const bool need_eval = act && mu_changed;   // barrier function of the current point for the new mu
-            if (vote_any<G>(need_eval)) {
+            if (vote_any<G>(T, need_eval)) {
                 T.on = need_eval;
-                eval_point<NT, G, false>(T, cta, cfg, ism, 0.0, mu);
+                eval_point<NT, G>(T, cta, cfg, ism, w.z, w.sl, mu);
                 if (need_eval) { theta = ism.es.theta; phi = ism.es.phi; }
             }
         }
@@ -1192,9 +881,19 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
         double alpha = amax, ft = f, th_t = theta, ph_t = phi;
         int accepted = 0, armijo = 0;
         bool pend = act;
-        while (vote_any<G>(pend)) {
+        while (vote_any<G>(T, pend)) {
             T.on = pend;
-            eval_point<NT, G, true>(T, cta, cfg, ism, alpha, mu);  // forms the trial point (zt, slt) on the fly
+            CMPC_LANES
+                {
+                    double* __restrict__ zt = w.zt; const double* __restrict__ z = w.z; const double* __restrict__ dz = w.dz;
+                    double* __restrict__ slt = w.slt; const double* __restrict__ sl = w.sl; const double* __restrict__ dsl = w.dsl;
+                    CMPC_UNROLL4
+                    for (int i = lane; i < (N + 1) * ZS; i += NT) zt[i] = z[i] + alpha * dz[i];
+                    CMPC_UNROLL4
+                    for (int i = lane; i < N * PS; i += NT) slt[i] = sl[i] + alpha * dsl[i];
+                }
+            CMPC_LANES_END
+            eval_point<NT, G>(T, cta, cfg, ism, w.zt, w.slt, mu);
             if (pend) {
                 ft = ism.es.f; th_t = ism.es.theta; ph_t = ism.es.phi;
                 bool ok = (fabs(ph_t) < HUGE_VAL) && (fabs(th_t) < HUGE_VAL) && th_t <= theta_max;
@@ -1230,13 +929,33 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
             if (!armijo && nfilt < MAX_FILTER) nfilt++;
             f = ft; theta0 = th_t; phi0 = ph_t;
         }
-        accept_pass<NT, G>(T, cfg, ism, mu, alpha, az);
+        CMPC_LANES
+            {
+                // every load of an item is issued before anything depends on it: one memory round trip per item
+                double* __restrict__ yp = w.yp; double* __restrict__ zlp = w.zl; double* __restrict__ zup = w.zu;
+                const double* __restrict__ lo = w.lo; const double* __restrict__ up = w.up; const double* __restrict__ slp = w.sl;
+                const double* __restrict__ dyp = w.dyp; const double* __restrict__ dzl = w.dzl; const double* __restrict__ dzu = w.dzu;
+                CMPC_UNROLL2
+                for (int i = lane; i < N * PS; i += NT) {
+                    const double sl = lo[i], su = up[i], s = slp[i], y = yp[i], dy = dyp[i], zl0 = zlp[i], dl = dzl[i], zu0 = zup[i], du = dzu[i];
+                    const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
+                    const bool ineq = (hl || hu) && !(sl == su);
+                    yp[i] = y + alpha * dy;
+                    const double ddl = s - sl, ddu = su - s;
+                    const double zl1 = fmax(fmin(zl0 + az * dl, KAPPA_SIGMA * mu / ddl), mu / (KAPPA_SIGMA * ddl));
+                    const double zu1 = fmax(fmin(zu0 + az * du, KAPPA_SIGMA * mu / ddu), mu / (KAPPA_SIGMA * ddu));
+                    if (ineq && hl) zlp[i] = zl1;
+                    if (ineq && hu) zup[i] = zu1;
+                }
+            }
+            for (int i = lane; i < (N + 1) * ES; i += NT) w.lam[i] += alpha * w.dlam[i];
+        CMPC_LANES_END
         CMPC_TOC(9)
         if (act) ++it;
 
         // ---- write-back of the instances that finished in this round (solution to the CasADi order), then back to the queue
         const bool done = fin >= 0;
-        if (vote_any<G>(done)) {
+        if (vote_any<G>(T, done)) {
             T.on = done && fin != 4;  // rejected input: x is left untouched
     CMPC_LANES
         for (int i2 = lane; i2 < (N + 1) * 64; i2 += NT) {

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(NT * G, CTAS)
 cmpc_solve_team_kernel(const __grid_constant__ Config cfg, int batch, const double* __restrict__ p,
                        const double* __restrict__ lbg, const double* __restrict__ ubg, double* x, double* lam, double* obj,
                        int* status, int* iters, int warm_duals, double* work, size_t work_stride, unsigned int* counter,
-                       const unsigned short* __restrict__ cmap)
+                       const unsigned short* __restrict__ cmap, int ngroups)
 {
     extern __shared__ __align__(16) double smem_raw[];
     const int team = threadIdx.x / NT;
@@ -153,6 +154,13 @@ cmpc_solve_team_kernel(const __grid_constant__ Config cfg, int batch, const doub
     T.lane = threadIdx.x - team * NT;
     T.id = team;
     T.on = true;
+    {   // lock-step groups: team t belongs to group t * ngroups / G (4 + 3 teams for G = 7, ngroups = 2); barriers 8 + group
+        const int g = team * ngroups / G;
+        int cnt = 0;
+        for (int t = 0; t < G; ++t) cnt += (t * ngroups / G == g) ? 1 : 0;
+        T.gbar = 8 + g;
+        T.gcount = cnt * NT;
+    }
     ISmem& sm = reinterpret_cast<ISmem*>(smem_raw)[team];
     typename TeamCta<NT, G>::type cta;
     cta.tid = T.lane; cta.nt = NT; cta.warp = T.lane >> 5; cta.lane = T.lane & 31; cta.wsize = 32;
@@ -363,6 +371,9 @@ using namespace cmpc;
 #ifndef CMPC_CTAS_PER_SM
 #define CMPC_CTAS_PER_SM 7
 #endif
+#ifndef CMPC_DEFAULT_GROUPS
+#define CMPC_DEFAULT_GROUPS 3     // independent lock-step groups per CTA (3 + 2 + 2 teams)
+#endif
 #ifndef CMPC_DEFAULT_LOCKSTEP
 #define CMPC_DEFAULT_LOCKSTEP 7   // teams per CTA of the default (team 96) configuration; 1 = independent teams
 #endif
@@ -381,6 +392,7 @@ static const void* team_kernel(int nt, int g)
 struct cmpc_handle_s {
     Config cfg;
     cmpc_config user;
+    int groups = 1;  // independent lock-step groups inside a CTA
     int device = 0, sm_count = 0, lockstep = 1, threads = CMPC_DEFAULT_TEAM, ctas_per_sm = 0, grid = 0, smem = 0;
     size_t work_stride = 0, work_slots = 0;
     double* d_work = nullptr;
@@ -490,6 +502,10 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
     // threads_per_instance: team size (0 = default); teams_per_cta: teams walking in lock-step through one CTA (0 = default)
     h->threads = u->threads_per_instance == 0 ? CMPC_DEFAULT_TEAM : u->threads_per_instance;
     h->lockstep = u->teams_per_cta == 0 ? (u->threads_per_instance == 0 ? CMPC_DEFAULT_LOCKSTEP : 1) : u->teams_per_cta;
+    h->groups = CMPC_DEFAULT_GROUPS;
+    if (const char* gs = getenv("CMPC_GROUPS")) h->groups = atoi(gs);  // experiments
+    if (h->groups < 1) h->groups = 1;
+    if (h->groups > h->lockstep) h->groups = h->lockstep;
     const void* kfn = team_kernel(h->threads, h->lockstep);
     if (!kfn) { delete h; return CMPC_E_INVALID; }
     h->smem = (int)sizeof(ISmem) * h->lockstep;
@@ -555,7 +571,7 @@ int cmpc_solve_batched(cmpc_handle h, int batch, const double* d_p, const double
     if (h->threads == NT && h->lockstep == G)                                                                            \
         cmpc_solve_team_kernel<NT, G, C><<<grid, NT * G, h->smem, st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj, \
                                                                         d_status, d_iters, warm_duals, h->d_work,         \
-                                                                        h->work_stride, h->d_counter, h->d_cmap);
+                                                                        h->work_stride, h->d_counter, h->d_cmap, h->groups);
     CMPC_FOR_EACH_KERNEL(X)
 #undef X
     h->launches++;
