@@ -37,7 +37,7 @@ data = rows[hi + 1:]
 assert len(data) == len(seq), (len(data), len(seq))
 # function table from the sources
 funcs = {}
-srcdir = os.path.join(os.path.dirname(lib), "csrc")
+srcdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "paper_romualdi_2022_icra_centroidal-mpc-walking_b200", "csrc")
 for fn in os.listdir(srcdir):
     starts = []
     for i, l in enumerate(open(os.path.join(srcdir, fn)), 1):
@@ -61,6 +61,8 @@ def func_of(file, ln):
 STALLS = ["stall_barrier", "stall_long_sb", "stall_short_sb", "stall_wait", "stall_selected", "stall_branch_resolving", "stall_no_inst", "stall_math", "stall_mio", "stall_lg", "stall_not_selected"]
 sidx = [hdr.index(s_) if s_ in hdr else None for s_ in STALLS]
 stall_line = collections.defaultdict(lambda: [0] * len(STALLS))
+wf_line = collections.Counter()
+iwf = hdr.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in hdr else None
 by_line, by_func = collections.Counter(), collections.Counter()
 samp_line, samp_func = collections.Counter(), collections.Counter()
 tot_i = tot_s = 0
@@ -68,6 +70,8 @@ for (ln, txt), r in zip(seq, data):
     n = int(float(r[ci] or 0)); s = int(float(r[cs] or 0))
     key = ln or ("?", 0)
     by_line[key] += n; samp_line[key] += s
+    if iwf is not None and r[iwf]:
+        wf_line[key] += int(float(r[iwf]))
     for q, ix in enumerate(sidx):
         if ix is not None and r[ix]:
             stall_line[key][q] += int(float(r[ix]))
@@ -95,4 +99,5 @@ if ph:
         n = sum(v for (f, l), v in by_line.items() if f == fn and lo <= l <= hi)
         s = sum(v for (f, l), v in samp_line.items() if f == fn and lo <= l <= hi)
         st = [sum(v[q] for (f, l), v in stall_line.items() if f == fn and lo <= l <= hi) for q in range(len(STALLS))]
-        print(f"{name:28s} {100*n/tot_i:6.2f}% {100*s/max(tot_s,1):6.2f}%  | " + " ".join(f"{100*x/max(tot_s,1):5.2f}" for x in st))
+        wf = sum(v for (f, l), v in wf_line.items() if f == fn and lo <= l <= hi)
+        print(f"{name:28s} {100*n/tot_i:6.2f}% {100*s/max(tot_s,1):6.2f}% smem-wf {100*wf/max(sum(wf_line.values()),1):5.1f}%  | " + " ".join(f"{100*x/max(tot_s,1):5.2f}" for x in st))

@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 PKG = "paper_romualdi_2022_icra_centroidal-mpc-walking_b200"
 pkg = importlib.import_module(PKG)
-pkg.LIB_PATH = os.path.join(ROOT, "profiles", "_build", "libcmpc_prof.so")
+pkg.LIB_PATH = os.environ.get("CMPC_PROF_LIB", os.path.join(ROOT, "profiles", "_build", "libcmpc_prof.so"))
 wl = importlib.import_module(PKG + ".workloads")
 import torch
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
