@@ -34,6 +34,16 @@ namespace cmpc {
 #define CMPC_ROLES(nroles) for (int r = lane & 31; r < (nroles); r += 32)
 #define CMPC_KNOTS(kfirst, klast) for (int k = (kfirst) + (lane >> 5); k <= (klast); k += (NT >= 32 ? NT / 32 : 1))
 
+// the per-variable entry functions: inlined into the role-major loops (role decoding hoisted) or shared out-of-line copies
+#ifndef CMPC_INLINE_ENTRIES
+#define CMPC_INLINE_ENTRIES 1
+#endif
+#if CMPC_INLINE_ENTRIES
+#define CMPC_ENTRY CMPC_HD
+#else
+#define CMPC_ENTRY CMPC_FN
+#endif
+
 constexpr int PS = 40;  // stride of a knot in the path-row arrays: friction 0..31 (16 c + 4 j + r) | step box 32..37 (32 + 3 c + q) | pad
 // per-knot table of constants
 constexpr int TS = 100;
@@ -118,7 +128,7 @@ CMPC_HD double path_dot(const double* tab, const double* zk, const double* zk1, 
 }
 
 // gradient of the objective in variable v (0..44) of knot k at the point zsrc
-CMPC_HD double grad_entry(const Config& cfg, const WorkS& w, const double* zsrc, int k, int v)
+CMPC_ENTRY double grad_entry(const Config& cfg, const WorkS& w, const double* zsrc, int k, int v)
 {
     const int N = cfg.N;
     const double* t = w.tab + k * TS;
@@ -143,7 +153,7 @@ CMPC_HD double grad_entry(const Config& cfg, const WorkS& w, const double* zsrc,
 }
 
 // (J' y)[variable v of knot k] for multipliers lam (equality rows, stage major) and yp (path rows); needs sd / aw at the iterate
-CMPC_HD double jty_entry(const Config& cfg, const WorkS& w, const double* lam, const double* yp, int k, int v)
+CMPC_ENTRY double jty_entry(const Config& cfg, const WorkS& w, const double* lam, const double* yp, int k, int v)
 {
     const int N = cfg.N;
     if (v < NS) {
@@ -177,7 +187,7 @@ CMPC_HD double jty_entry(const Config& cfg, const WorkS& w, const double* lam, c
 }
 
 // (W dz)[variable v of knot k]: hessian of the lagrangian (nlp_hess_l, tmp.c:58926) + delta_w I, times the step
-CMPC_HD double hess_dz_entry(const Config& cfg, const WorkS& w, double dw, int k, int v)
+CMPC_ENTRY double hess_dz_entry(const Config& cfg, const WorkS& w, double dw, int k, int v)
 {
     const int N = cfg.N;
     const double* t = w.tab + k * TS;
