@@ -426,8 +426,8 @@ CMPC_FN void barrier_pass(Team T, const Config& cfg, const WorkS& w, double mu, 
                     if (sl == su) { sg = 1.0 / dc; t = y + (g - sl) / dc; }
                     else {
                         sg = dw;
-                        if (hl) { const double dd = s - sl; sg += zl / dd; t -= mu / dd; }
-                        if (hu) { const double dd = su - s; sg += zu / dd; t += mu / dd; }
+                        if (hl) { const double rd = 1.0 / (s - sl); sg += zl * rd; t -= mu * rd; }
+                        if (hu) { const double rd = 1.0 / (su - s); sg += zu * rd; t += mu * rd; }
                         if (hl && !hu) t += KAPPA_D * mu;
                         if (hu && !hl) t -= KAPPA_D * mu;
                         t += sg * (g - s);
@@ -509,8 +509,8 @@ CMPC_FN void recover_pass(Team T, const Config& cfg, const WorkS& w, double mu, 
                         const double s = w.sl[pr];
                         ds = jd + (w.gp[pr] - s);  // (g - s) first: jd can be below ulp(g)
                         double rs = -w.yp[pr];
-                        if (hl) { const double dd = s - sl; rs -= mu / dd; dzl = mu / dd - w.zl[pr] - w.zl[pr] / dd * ds; }
-                        if (hu) { const double dd = su - s; rs += mu / dd; dzu = mu / dd - w.zu[pr] + w.zu[pr] / dd * ds; }
+                        if (hl) { const double rd = 1.0 / (s - sl), zl = w.zl[pr]; rs -= mu * rd; dzl = mu * rd - zl - zl * rd * ds; }
+                        if (hu) { const double rd = 1.0 / (su - s), zu = w.zu[pr]; rs += mu * rd; dzu = mu * rd - zu + zu * rd * ds; }
                         if (hl && !hu) rs += KAPPA_D * mu;
                         if (hu && !hl) rs -= KAPPA_D * mu;
                         dy = w.sig[pr] * ds + rs;
@@ -945,15 +945,15 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
                 double* __restrict__ yp = w.yp; double* __restrict__ zlp = w.zl; double* __restrict__ zup = w.zu;
                 const double* __restrict__ lo = w.lo; const double* __restrict__ up = w.up; const double* __restrict__ slp = w.sl;
                 const double* __restrict__ dyp = w.dyp; const double* __restrict__ dzl = w.dzl; const double* __restrict__ dzu = w.dzu;
-                CMPC_UNROLL2
+                CMPC_ROLLED
                 for (int i = lane; i < N * PS; i += NT) {
                     const double sl = lo[i], su = up[i], s = slp[i], y = yp[i], dy = dyp[i], zl0 = zlp[i], dl = dzl[i], zu0 = zup[i], du = dzu[i];
                     const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
                     const bool ineq = (hl || hu) && !(sl == su);
                     yp[i] = y + alpha * dy;
-                    const double ddl = s - sl, ddu = su - s;
-                    const double zl1 = fmax(fmin(zl0 + az * dl, KAPPA_SIGMA * mu / ddl), mu / (KAPPA_SIGMA * ddl));
-                    const double zu1 = fmax(fmin(zu0 + az * du, KAPPA_SIGMA * mu / ddu), mu / (KAPPA_SIGMA * ddu));
+                    const double rl = 1.0 / (s - sl), ru = 1.0 / (su - s);  // one division per bound (footprint: an IEEE division is ~35 instructions)
+                    const double zl1 = fmax(fmin(zl0 + az * dl, (KAPPA_SIGMA * mu) * rl), (mu / KAPPA_SIGMA) * rl);
+                    const double zu1 = fmax(fmin(zu0 + az * du, (KAPPA_SIGMA * mu) * ru), (mu / KAPPA_SIGMA) * ru);
                     if (ineq && hl) zlp[i] = zl1;
                     if (ineq && hu) zup[i] = zu1;
                 }

@@ -76,11 +76,17 @@ struct DevCta {
         for (int k = 0; k < K; ++k) {
             const int op = k < KM ? 0 : (k < KM + KN ? 1 : 2);
             double* dst = k < KM ? vmax + k : (k < KM + KN ? vmin + (k - KM) : vsum + (k - KM - KN));
-            double x = red[k];
-            for (int w2 = 1; w2 < nw; ++w2) x = combine_op(x, red[w2 * K + k], op);
-            *dst = x;
+            *dst = combine_warps(red + k, K, nw, op);
         }
         bsync();
+    }
+    // statistic k of all warps (one copy of the code: the passes are bound by their instruction footprint)
+    static __device__ __noinline__ double combine_warps(const double* red, int K, int nw, int op)
+    {
+        double x = red[0];
+#pragma unroll 1
+        for (int w2 = 1; w2 < nw; ++w2) x = combine_op(x, red[w2 * K], op);
+        return x;
     }
     static __device__ __forceinline__ double combine_op(double x, double y, int op)
     {
