@@ -35,7 +35,7 @@ PKG = "paper_romualdi_2022_icra_centroidal-mpc-walking_b200"
 # profiles/ and DESIGN.md "flop accounting"), and the canonical dense figure of SURVEY.md 8(d)
 FLOP_EXEC_PER_ITER_KNOT = 1.22e5
 FLOP_CANON_PER_ITER_KNOT = 422275.0
-DRAM_TRAFFIC_PER_LAUNCH = 1.127e10   # bytes, ncu (icub3_b1024, team 96)
+DRAM_TRAFFIC_PER_LAUNCH = 1.240e10   # bytes, ncu capture prof_g3 (icub3_b1024, team 96, 7 teams / CTA in 3 groups)
 FP64_PEAK_FALLBACK_TFLOPS = 37.0  # vendor figure (HGX B200 296 TF / 8); used only if the live DFMA probe fails
 
 
@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--team", type=int, default=0, help="threads per instance (32/64/96/128), 0 = library default")
     ap.add_argument("--lockstep", type=int, default=0, help="teams per CTA walking in lock-step (1, 3, 7; 0 = library default)")
+    ap.add_argument("--groups", type=int, default=0, help="independent lock-step groups per CTA (0 = library default)")
     ap.add_argument("--identical", action="store_true", help="experiment: every instance is a copy of instance 0")
     ap.add_argument("--ctas", type=int, default=0, help="resident teams per SM (0 = occupancy)")
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (0 = the workload's own size)")
@@ -185,6 +186,7 @@ def main():
     cfg.threads_per_instance = args.team
     cfg.ctas_per_sm = args.ctas
     cfg.teams_per_cta = args.lockstep
+    cfg.lockstep_groups = args.groups
     solver = pkg.BatchedCentroidalMPC(cfg)
     B, N = w["p"].shape[0], cfg.horizon
     n, m, npar = solver.L.n, solver.L.m, solver.L.np
@@ -327,7 +329,7 @@ def main():
                         "iterations": int(iters_h[0]), "note": "batch of one instance, device resident, cold start"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "traffic": DRAM_TRAFFIC_PER_LAUNCH if (args.workload == "icub3_b1024" and B == 1024) else None,
-                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu capture prof_t96c "
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu capture prof_g3 "
                                          "(profiles/r1_notes.md): the solver's scratch (iterate vectors + Riccati factors of 1036 "
                                          "resident teams) does not fit the 126 MB L2", "peak_source": peak_src, "kernel": "cmpc_solve_team_kernel",
                          "kernel_ms_per_launch": 1e3 * kernel_s, "flop_executed_per_launch": flop_exec,
@@ -339,7 +341,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            sample = min(B, max(64, 32 * cores))   # about 10-30 core-seconds of CPU work
+            sample = min(B, max(64, 64 * cores))   # about 10-30 core-seconds of CPU work
             rate, dt, ok, its = cpu_oracle_rate(ocfg, w, sample, cores, args.tol)
             line["cpu_baseline"] = {"value": rate, "unit": "solves/s", "cores": cores, "kind": "port",
                                     "sample": f"first {sample} instances of the workload, {dt:.1f} s, {ok}/{sample} "

@@ -68,6 +68,8 @@ typedef struct cmpc_config {
     int threads_per_instance;               /* team size: 32, 64, 96 or 128 threads per instance, 0 = default (96)  */
     int ctas_per_sm;                        /* resident CTAs per SM used to size the persistent grid, 0 = occupancy */
     int teams_per_cta;                      /* teams walking in lock-step through one CTA: 1, 3 or 7; 0 = default    */
+    int lockstep_groups;                    /* independent lock-step groups the teams of a CTA form: 1 .. teams_per_cta, */
+                                            /* 0 = default (3: groups of 3 + 2 + 2 teams)                              */
 } cmpc_config;
 
 typedef struct cmpc_handle_s* cmpc_handle;
@@ -136,6 +138,8 @@ const char* cmpc_error_string(int code);
 
 /* grid geometry chosen for the solver kernel (persistent CTAs): for reporting */
 int cmpc_solver_geometry(cmpc_handle h, int* grid_ctas, int* threads, int* smem_bytes, int* ctas_per_sm, int* sm_count);
+/* teams per CTA and the number of independent lock-step groups they form: for reporting */
+int cmpc_solver_lockstep(cmpc_handle h, int* teams_per_cta, int* lockstep_groups);
 
 #ifdef __cplusplus
 }

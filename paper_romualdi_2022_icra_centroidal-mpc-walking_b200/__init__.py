@@ -28,7 +28,7 @@ class CmpcConfig(C.Structure):
                 ("corners", C.c_double * 24), ("ipopt_tolerance", C.c_double), ("ipopt_max_iteration", C.c_int),
                 ("mu_init", C.c_double), ("bound_relax_factor", C.c_double), ("bound_push", C.c_double),
                 ("infinity", C.c_double), ("device", C.c_int), ("threads_per_instance", C.c_int),
-                ("ctas_per_sm", C.c_int), ("teams_per_cta", C.c_int)]
+                ("ctas_per_sm", C.c_int), ("teams_per_cta", C.c_int), ("lockstep_groups", C.c_int)]
 
 
 _dp = C.POINTER(C.c_double)
@@ -67,6 +67,7 @@ def load_library() -> C.CDLL:
     L.cmpc_error_string.argtypes = [i]
     L.cmpc_error_string.restype = C.c_char_p
     L.cmpc_solver_geometry.argtypes = [vp, _ip, _ip, _ip, _ip, _ip]
+    L.cmpc_solver_lockstep.argtypes = [vp, _ip, _ip]
     _lib = L
     return L
 
@@ -146,7 +147,10 @@ class BatchedCentroidalMPC:
     def geometry(self):
         v = [C.c_int() for _ in range(5)]
         self.lib.cmpc_solver_geometry(self.handle, *[C.byref(a) for a in v])
-        return dict(grid=v[0].value, threads=v[1].value, smem=v[2].value, ctas_per_sm=v[3].value, sm_count=v[4].value)
+        t, g = C.c_int(), C.c_int()
+        self.lib.cmpc_solver_lockstep(self.handle, C.byref(t), C.byref(g))
+        return dict(grid=v[0].value, threads=v[1].value, smem=v[2].value, ctas_per_sm=v[3].value, sm_count=v[4].value,
+                    teams_per_cta=t.value, lockstep_groups=g.value)
 
     def measure_fp64_peak(self) -> float:
         v = C.c_double()

@@ -508,8 +508,8 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
     // threads_per_instance: team size (0 = default); teams_per_cta: teams walking in lock-step through one CTA (0 = default)
     h->threads = u->threads_per_instance == 0 ? CMPC_DEFAULT_TEAM : u->threads_per_instance;
     h->lockstep = u->teams_per_cta == 0 ? (u->threads_per_instance == 0 ? CMPC_DEFAULT_LOCKSTEP : 1) : u->teams_per_cta;
-    h->groups = CMPC_DEFAULT_GROUPS;
-    if (const char* gs = getenv("CMPC_GROUPS")) h->groups = atoi(gs);  // experiments
+    h->groups = u->lockstep_groups > 0 ? u->lockstep_groups : CMPC_DEFAULT_GROUPS;
+    if (const char* gs = getenv("CMPC_GROUPS")) h->groups = atoi(gs);  // experiments (profiles/r1_notes.md)
     if (h->groups < 1) h->groups = 1;
     if (h->groups > h->lockstep) h->groups = h->lockstep;
     const void* kfn = team_kernel(h->threads, h->lockstep);
@@ -763,6 +763,14 @@ int cmpc_solver_geometry(cmpc_handle h, int* grid, int* threads, int* smem, int*
     if (smem) *smem = h->smem;
     if (ctas_per_sm) *ctas_per_sm = h->ctas_per_sm;
     if (sm_count) *sm_count = h->sm_count;
+    return CMPC_OK;
+}
+
+int cmpc_solver_lockstep(cmpc_handle h, int* teams_per_cta, int* lockstep_groups)
+{
+    if (!h) return CMPC_E_INVALID;
+    if (teams_per_cta) *teams_per_cta = h->lockstep;
+    if (lockstep_groups) *lockstep_groups = h->groups;
     return CMPC_OK;
 }
 

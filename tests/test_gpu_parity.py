@@ -274,3 +274,22 @@ def test_empty_batch_and_team_sizes(workloads, oracle):
         else:
             assert np.max(np.abs(x - ref[0])) < 1e-6 and np.max(np.abs(obj - ref[1]) / np.abs(ref[1])) < 1e-9
         s.close()
+
+
+def test_lockstep_groups_agree(workloads):
+    """the teams of a CTA walk in 1, 2, 3 or 7 independent lock-step groups (named barriers): same solutions, every instance
+    of a batch that spans several CTAs and leaves some teams without work"""
+    P = pkg()
+    w = workloads.walk_batch(N=12, B=45, seed=11, state_noise=1.5, yaw_range=0.2)
+    ref = None
+    for groups in (1, 2, 3, 7):
+        s = P.BatchedCentroidalMPC(P.ergocub_config(contact_position_weight=200.0, lockstep_groups=groups))
+        geo = s.geometry()
+        assert geo["teams_per_cta"] == 7 and geo["lockstep_groups"] == groups, geo
+        x, lam, obj, status, iters = s.solve_host(w["p"], w["lbg"], w["ubg"], w["x0"])
+        assert (status == 0).all(), status
+        if ref is None:
+            ref = (x, obj, iters)
+        else:
+            assert np.max(np.abs(x - ref[0])) < 1e-9 and np.array_equal(iters, ref[2])
+        s.close()
