@@ -399,6 +399,7 @@ struct cmpc_handle_s {
     Config cfg;
     cmpc_config user;
     int groups = 1;  // independent lock-step groups inside a CTA
+    bool latency_path = false;  // default geometry: batches of at most one instance per SM go to the single-team kernel
     int device = 0, sm_count = 0, lockstep = 1, threads = CMPC_DEFAULT_TEAM, ctas_per_sm = 0, grid = 0, smem = 0;
     size_t work_stride = 0, work_slots = 0;
     double* d_work = nullptr;
@@ -514,6 +515,8 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
     if (h->groups > h->lockstep) h->groups = h->lockstep;
     const void* kfn = team_kernel(h->threads, h->lockstep);
     if (!kfn) { delete h; return CMPC_E_INVALID; }
+    // small batches (at most one instance per SM) are latency bound: one team of 128 threads per CTA, no register cap
+    h->latency_path = u->threads_per_instance == 0 && u->teams_per_cta == 0 && !getenv("CMPC_NO_LATENCY_PATH");
     h->smem = (int)sizeof(ISmem) * h->lockstep;
     int occ = 0;
     e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
@@ -572,6 +575,14 @@ int cmpc_solve_batched(cmpc_handle h, int batch, const double* d_p, const double
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(h->device));
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
+    if (h->latency_path && batch <= h->sm_count && (size_t)batch <= h->work_slots) {
+        cmpc_solve_team_kernel<128, 1, 1><<<batch, 128, (int)sizeof(ISmem), st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj,
+                                                                                 d_status, d_iters, warm_duals, h->d_work,
+                                                                                 h->work_stride, h->d_counter, h->d_cmap, 1);
+        h->launches++;
+        CK(cudaGetLastError());
+        return CMPC_OK;
+    }
     int grid = std::min((batch + h->lockstep - 1) / h->lockstep, h->grid);
 #define X(NT, G, C)                                                                                                      \
     if (h->threads == NT && h->lockstep == G)                                                                            \

@@ -49,10 +49,15 @@ def compare_solutions(L, x, xo, obj, obj_o):
         assert err <= 1e-5, (name, err)
 
 
-@pytest.fixture(scope="module")
-def solver12():
+@pytest.fixture(scope="module", params=["auto", "lockstep7"])
+def solver12(request):
+    """default geometry (batches of at most one instance per SM take the single-team latency kernel) and the 7-team lock-step
+    kernel forced for every batch size: both must pass every parity test"""
     P = pkg()
-    s = P.BatchedCentroidalMPC(P.ergocub_config(contact_position_weight=200.0))  # weights of the reference's tmp.c
+    kw = dict(teams_per_cta=7) if request.param == "lockstep7" else {}
+    s = P.BatchedCentroidalMPC(P.ergocub_config(contact_position_weight=200.0, **kw))  # weights of the reference's tmp.c
+    geo = s.geometry()
+    assert geo["teams_per_cta"] == 7 and geo["threads"] == 96, geo
     yield s
     s.close()
 
@@ -283,7 +288,7 @@ def test_lockstep_groups_agree(workloads):
     w = workloads.walk_batch(N=12, B=45, seed=11, state_noise=1.5, yaw_range=0.2)
     ref = None
     for groups in (1, 2, 3, 7):
-        s = P.BatchedCentroidalMPC(P.ergocub_config(contact_position_weight=200.0, lockstep_groups=groups))
+        s = P.BatchedCentroidalMPC(P.ergocub_config(contact_position_weight=200.0, lockstep_groups=groups, teams_per_cta=7))
         geo = s.geometry()
         assert geo["teams_per_cta"] == 7 and geo["lockstep_groups"] == groups, geo
         x, lam, obj, status, iters = s.solve_host(w["p"], w["lbg"], w["ubg"], w["x0"])
