@@ -33,7 +33,7 @@ PKG = "paper_romualdi_2022_icra_centroidal-mpc-walking_b200"
 
 # FP64 flop executed per interior-point iteration and knot by cmpc_solve_kernel (measured with ncu, see
 # profiles/ and DESIGN.md "flop accounting"), and the canonical dense figure of SURVEY.md 8(d)
-FLOP_EXEC_PER_ITER_KNOT = 1.22e5
+FLOP_EXEC_PER_ITER_KNOT = {"monotone": 1.22e5, "mehrotra": 1.30e5}   # a predictor-corrector iteration has a second solve
 FLOP_CANON_PER_ITER_KNOT = 422275.0
 DRAM_TRAFFIC_PER_LAUNCH = 1.240e10   # bytes, ncu capture prof_g3 (icub3_b1024, team 96, 7 teams / CTA in 3 groups)
 FP64_PEAK_FALLBACK_TFLOPS = 37.0  # vendor figure (HGX B200 296 TF / 8); used only if the live DFMA probe fails
@@ -157,6 +157,8 @@ def main():
     ap.add_argument("--identical", action="store_true", help="experiment: every instance is a copy of instance 0")
     ap.add_argument("--ctas", type=int, default=0, help="resident teams per SM (0 = occupancy)")
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (0 = the workload's own size)")
+    ap.add_argument("--mu-strategy", default="mehrotra", choices=["mehrotra", "monotone"],
+                    help="barrier update of the solve: Mehrotra predictor-corrector (library default) or IPOPT's monotone update")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -187,6 +189,7 @@ def main():
     cfg.ctas_per_sm = args.ctas
     cfg.teams_per_cta = args.lockstep
     cfg.lockstep_groups = args.groups
+    cfg.mu_strategy = pkg.MU_MEHROTRA if args.mu_strategy == "mehrotra" else pkg.MU_MONOTONE
     solver = pkg.BatchedCentroidalMPC(cfg)
     B, N = w["p"].shape[0], cfg.horizon
     n, m, npar = solver.L.n, solver.L.m, solver.L.np
@@ -308,7 +311,7 @@ def main():
         except Exception:
             pass
         kernel_s = t_kernel / args.steps
-        flop_exec = total_iters * N * FLOP_EXEC_PER_ITER_KNOT
+        flop_exec = total_iters * N * FLOP_EXEC_PER_ITER_KNOT[args.mu_strategy]
         flop_canon = total_iters * N * FLOP_CANON_PER_ITER_KNOT
         achieved = flop_exec / kernel_s / 1e12
         alg_bytes = 8.0 * B * (npar + 2 * m + 2 * n + 2 * m)
@@ -317,6 +320,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "instances_per_gpu": B, "horizon_knots": N, "ipopt_tolerance": args.tol,
+                       "mu_strategy": args.mu_strategy,
                        "robot_ini": "iCubGazeboV3/centroidal_mpc.ini" if args.workload.startswith("icub3") else
                                     "ergoCubGazeboV1_1/centroidal_mpc.ini",
                        "cold_start": True, "l2": "flushed between steps (256 MB write)",

@@ -70,7 +70,16 @@ typedef struct cmpc_config {
     int teams_per_cta;                      /* teams walking in lock-step through one CTA: 1, 3 or 7; 0 = default    */
     int lockstep_groups;                    /* independent lock-step groups the teams of a CTA form: 1 .. teams_per_cta, */
                                             /* 0 = default (3: groups of 3 + 2 + 2 teams)                              */
+    int mu_strategy;                        /* barrier-parameter update of the interior-point solve:                     */
+                                            /* CMPC_MU_DEFAULT (0) = CMPC_MU_MEHROTRA; CMPC_MU_MONOTONE = IPOPT's default */
+                                            /* Fiacco-McCormick update (iterate-for-iterate the reference's solver path); */
+                                            /* CMPC_MU_MEHROTRA = predictor-corrector (mu from the affine-scaling step,   */
+                                            /* second-order corrector on the same factorisation, ~0.63 x the iterations;  */
+                                            /* same termination test; an instance it cannot finish is re-solved monotone) */
 } cmpc_config;
+#define CMPC_MU_DEFAULT 0
+#define CMPC_MU_MONOTONE 1
+#define CMPC_MU_MEHROTRA 2
 
 typedef struct cmpc_handle_s* cmpc_handle;
 

@@ -73,6 +73,10 @@ typedef struct cmpc_oracle_ipm_opts {
     double inf_bound;        /* |b| >= inf_bound means no bound (nlp_*_bound_inf 1e19)            */
     int warm_duals;          /* 1: use lam_g on entry as initial multipliers                      */
     int verbose;
+    int mehrotra;            /* 0: IPOPT's default monotone barrier update (the restatement of the reference's solve);
+                              * 1: Mehrotra predictor-corrector barrier update (mu from the affine-scaling step, second-order
+                              *    corrector with the same factorisation), the mu strategy of the CUDA path's default mode;
+                              *    instances it cannot finish are re-solved on the monotone path                       */
 } cmpc_oracle_ipm_opts;
 
 void cmpc_oracle_ipm_default_opts(cmpc_oracle_ipm_opts* o);
@@ -85,6 +89,7 @@ typedef struct cmpc_oracle_ipm_stats {
     double dual_inf, constr_viol, compl_inf; /* unscaled components          */
     int n_reg;          /* iterations that needed delta_w > 0                */
     int n_ls_trials;    /* total backtracking trials                         */
+    int n_fallback;     /* 1: the predictor-corrector run failed, monotone re-solve */
 } cmpc_oracle_ipm_stats;
 
 /* callbacks so that the same IPM can run on the restated NLP or on the compiled reference functions */

@@ -48,6 +48,7 @@ void cmpc_oracle_ipm_default_opts(cmpc_oracle_ipm_opts* o)
     o->inf_bound = 1e19;
     o->warm_duals = 0;
     o->verbose = 0;
+    o->mehrotra = 0;
 }
 
 /* IPOPT constants (defaults of 3.13/3.14) */
@@ -201,6 +202,7 @@ typedef struct ipm_ws {
     double *grad, *g, *jnz, *hnz;
     double *xt, *st, *gt;                   /* trial */
     double *rhs, *sigma, *rs, *rd;
+    double *muL, *muU;                      /* complementarity target of every bound (mu, or mu -+ the Mehrotra corrector) */
     /* KKT ordering */
     int nK; int* perm; /* unknown u (0..nK-1: x then eq slots) -> position */
     band K;
@@ -315,8 +317,8 @@ static int solve_kkt(ipm_ws* W, double mu, double dw, double dc, double lam_f)
         } else {
             int i = W->rslot[r];
             double sg = dw, rs = -W->y[r];
-            if (W->hasL[i]) { double d = W->s[i] - W->sL[i]; sg += W->zL[i] / d; rs -= mu / d; }
-            if (W->hasU[i]) { double d = W->sU[i] - W->s[i]; sg += W->zU[i] / d; rs += mu / d; }
+            if (W->hasL[i]) { double d = W->s[i] - W->sL[i]; sg += W->zL[i] / d; rs -= W->muL[i] / d; }
+            if (W->hasU[i]) { double d = W->sU[i] - W->s[i]; sg += W->zU[i] / d; rs += W->muU[i] / d; }
             if (W->hasL[i] && !W->hasU[i]) rs += KAPPA_D * mu;
             if (W->hasU[i] && !W->hasL[i]) rs -= KAPPA_D * mu;
             double rd = W->g[r] - W->s[i];
@@ -362,8 +364,8 @@ static int solve_kkt(ipm_ws* W, double mu, double dw, double dc, double lam_f)
             W->ds[i] = ds;
             W->dy[r] = W->sigma[i] * ds + W->rs[i];
             W->dzL[i] = W->dzU[i] = 0;
-            if (W->hasL[i]) { double d = W->s[i] - W->sL[i]; W->dzL[i] = mu / d - W->zL[i] - W->zL[i] / d * ds; }
-            if (W->hasU[i]) { double d = W->sU[i] - W->s[i]; W->dzU[i] = mu / d - W->zU[i] + W->zU[i] / d * ds; }
+            if (W->hasL[i]) { double d = W->s[i] - W->sL[i]; W->dzL[i] = W->muL[i] / d - W->zL[i] - W->zL[i] / d * ds; }
+            if (W->hasU[i]) { double d = W->sU[i] - W->s[i]; W->dzU[i] = W->muU[i] / d - W->zU[i] + W->zU[i] / d * ds; }
             curv += W->sigma[i] * ds * ds; dd += ds * ds;
             yc += (W->y[r] + W->dy[r]) * W->rd[i];
         }
@@ -385,19 +387,16 @@ static void ws_free(ipm_ws* W)
     free(W->x); free(W->s); free(W->y); free(W->zL); free(W->zU);
     free(W->dx); free(W->ds); free(W->dy); free(W->dzL); free(W->dzU);
     free(W->grad); free(W->g); free(W->jnz); free(W->hnz); free(W->xt); free(W->st); free(W->gt);
-    free(W->rhs); free(W->sigma); free(W->rs); free(W->rd); free(W->perm);
+    free(W->rhs); free(W->sigma); free(W->rs); free(W->rd); free(W->perm); free(W->muL); free(W->muU);
     band_free(&W->K);
 }
 
 #define ALLOCD(k) calloc((size_t)((k) > 0 ? (k) : 1), sizeof(double))
 #define ALLOCI(k) calloc((size_t)((k) > 0 ? (k) : 1), sizeof(int))
 
-int cmpc_oracle_ipm_solve_fn(const cmpc_oracle_nlp_fn* F, int N, const cmpc_oracle_ipm_opts* opts, const double* p,
-                             const double* lbg, const double* ubg, double* x, double* lam_g,
-                             cmpc_oracle_ipm_stats* stats)
+static int ipm_core(const cmpc_oracle_nlp_fn* F, int N, const cmpc_oracle_ipm_opts* opts, int mehrotra, const double* p,
+                    const double* lbg, const double* ubg, double* x, double* lam_g, cmpc_oracle_ipm_stats* stats)
 {
-    cmpc_oracle_ipm_opts defo;
-    if (!opts) { cmpc_oracle_ipm_default_opts(&defo); opts = &defo; }
     ipm_ws Wk; ipm_ws* W = &Wk; memset(W, 0, sizeof *W);
     const int n = F->n, m = F->m;
     W->n = n; W->m = m; W->N = N; W->nlp = F;
@@ -444,6 +443,7 @@ int cmpc_oracle_ipm_solve_fn(const cmpc_oracle_nlp_fn* F, int N, const cmpc_orac
     W->grad = ALLOCD(n); W->g = ALLOCD(m); W->jnz = ALLOCD(F->nnz_j); W->hnz = ALLOCD(F->nnz_h);
     W->xt = ALLOCD(n); W->st = ALLOCD(mI); W->gt = ALLOCD(m);
     W->nK = n + mE;
+    W->muL = ALLOCD(mI); W->muU = ALLOCD(mI);
     W->rhs = ALLOCD(W->nK); W->sigma = ALLOCD(mI); W->rs = ALLOCD(mI); W->rd = ALLOCD(mI);
     /* stage ordering + bandwidth */
     W->perm = ALLOCI(W->nK);
@@ -511,8 +511,8 @@ int cmpc_oracle_ipm_solve_fn(const cmpc_oracle_nlp_fn* F, int N, const cmpc_orac
                     e0.viol, e0.compl_, mu, dw_last);
         if (e0.E <= opts->tol && e0.dual <= 1.0 && e0.viol <= 1e-4 && e0.compl_ <= 1e-4) { status = 0; break; }
         if (it == opts->max_iter) { status = 1; break; }
-        /* barrier parameter update (eq. 7) */
-        for (;;) {
+        /* barrier parameter update (eq. 7); in predictor-corrector mode mu follows from the affine step below */
+        while (!mehrotra) {
             errs em = kkt_error(W, mu, scratch);
             if (em.E <= KAPPA_EPS * mu && mu > mu_min) {
                 mu = fmax(mu_min, fmin(KAPPA_MU * mu, pow(mu, THETA_MU)));
@@ -524,8 +524,9 @@ int cmpc_oracle_ipm_solve_fn(const cmpc_oracle_nlp_fn* F, int N, const cmpc_orac
         F->hess(F->ctx, W->x, p, 1.0, W->y, W->hnz);
         double dc = DC_BAR * pow(mu, KAPPA_C);
         double dw = 0.0; int rc, tries = 0;
+        for (int i = 0; i < mI; ++i) W->muL[i] = W->muU[i] = mehrotra ? 0.0 : mu;   /* predictor: affine-scaling step */
         for (;;) {
-            rc = solve_kkt(W, mu, dw, dc, 1.0);
+            rc = solve_kkt(W, mehrotra ? 0.0 : mu, dw, dc, 1.0);
             if (rc == 0) break;
             if (dw == 0.0) dw = dw_last == 0.0 ? DW_FIRST : fmax(DW_MIN, KW_MINUS * dw_last);
             else dw *= (dw_last == 0.0 ? KW_PLUS_FIRST : KW_PLUS);
@@ -533,6 +534,39 @@ int cmpc_oracle_ipm_solve_fn(const cmpc_oracle_nlp_fn* F, int N, const cmpc_orac
         }
         if (rc != 0) { status = 3; break; }
         if (dw > 0.0) { dw_last = dw; stats->n_reg++; }
+        if (mehrotra) {
+            /* Mehrotra's rule: step lengths to the boundary of the affine step, mu_aff = mean complementarity after it,
+             * sigma = (mu_aff / mu_cur)^3, new barrier parameter sigma mu_cur; corrector = second solve with the SAME matrix
+             * and the complementarity targets  mu - ds_aff dz_aff  (second-order term of (s + ds)(z + dz) = mu) */
+            double ap = 1.0, ad = 1.0, s00 = 0, s10 = 0, s01 = 0, s11 = 0; int nb = 0;
+            for (int i = 0; i < mI; ++i) {
+                if (W->hasL[i]) {
+                    double d = W->s[i] - W->sL[i];
+                    if (W->ds[i] < 0) ap = fmin(ap, -d / W->ds[i]);
+                    if (W->dzL[i] < 0) ad = fmin(ad, -W->zL[i] / W->dzL[i]);
+                    s00 += d * W->zL[i]; s10 += W->ds[i] * W->zL[i]; s01 += d * W->dzL[i]; s11 += W->ds[i] * W->dzL[i]; nb++;
+                }
+                if (W->hasU[i]) {
+                    double d = W->sU[i] - W->s[i];
+                    if (W->ds[i] > 0) ap = fmin(ap, d / W->ds[i]);
+                    if (W->dzU[i] < 0) ad = fmin(ad, -W->zU[i] / W->dzU[i]);
+                    s00 += d * W->zU[i]; s10 -= W->ds[i] * W->zU[i]; s01 += d * W->dzU[i]; s11 -= W->ds[i] * W->dzU[i]; nb++;
+                }
+            }
+            if (nb > 0 && s00 > 0.0) {
+                double aff = s00 + ap * s10 + ad * s01 + ap * ad * s11;
+                double sg = fmin(1.0, fmax(0.0, aff / s00));
+                mu = fmax(mu_min, sg * sg * sg * s00 / nb);
+            }
+            tau = fmax(TAU_MIN, 1.0 - mu);
+            nfilt = 0;
+            for (int i = 0; i < mI; ++i) {
+                W->muL[i] = mu - W->ds[i] * W->dzL[i];
+                W->muU[i] = mu + W->ds[i] * W->dzU[i];
+            }
+            rc = solve_kkt(W, mu, dw, dc, 1.0);
+            if (rc == 1) { status = 3; break; }
+        }
         /* fraction to the boundary (eq. 15) */
         double amax = 1.0, az = 1.0;
         for (int i = 0; i < mI; ++i) {
@@ -624,6 +658,31 @@ int cmpc_oracle_ipm_solve_fn(const cmpc_oracle_nlp_fn* F, int N, const cmpc_orac
     stats->kkt_error = e0.E; stats->dual_inf = e0.dual; stats->constr_viol = e0.viol; stats->compl_inf = e0.compl_;
     ws_free(W);
     return status;
+}
+
+int cmpc_oracle_ipm_solve_fn(const cmpc_oracle_nlp_fn* F, int N, const cmpc_oracle_ipm_opts* opts, const double* p,
+                             const double* lbg, const double* ubg, double* x, double* lam_g,
+                             cmpc_oracle_ipm_stats* stats)
+{
+    cmpc_oracle_ipm_opts defo;
+    if (!opts) { cmpc_oracle_ipm_default_opts(&defo); opts = &defo; }
+    if (!opts->mehrotra) return ipm_core(F, N, opts, 0, p, lbg, ubg, x, lam_g, stats);
+    /* predictor-corrector mode; an instance it cannot finish (line-search / numerical failure, iteration limit) is solved
+     * again from the same initial point on the monotone path */
+    double* x0 = malloc(sizeof(double) * F->n);
+    double* l0 = lam_g ? malloc(sizeof(double) * F->m) : NULL;
+    memcpy(x0, x, sizeof(double) * F->n);
+    if (lam_g) memcpy(l0, lam_g, sizeof(double) * F->m);
+    int st = ipm_core(F, N, opts, 1, p, lbg, ubg, x, lam_g, stats);
+    if (st >= 1 && st <= 3) {
+        cmpc_oracle_ipm_stats s1 = *stats;
+        memcpy(x, x0, sizeof(double) * F->n);
+        if (lam_g) memcpy(lam_g, l0, sizeof(double) * F->m);
+        st = ipm_core(F, N, opts, 0, p, lbg, ubg, x, lam_g, stats);
+        stats->iters += s1.iters; stats->n_reg += s1.n_reg; stats->n_ls_trials += s1.n_ls_trials; stats->n_fallback = 1;
+    }
+    free(x0); free(l0);
+    return st;
 }
 
 /* ------------------------------------------------------------------ adapters */

@@ -28,12 +28,16 @@ class CmpcConfig(C.Structure):
                 ("corners", C.c_double * 24), ("ipopt_tolerance", C.c_double), ("ipopt_max_iteration", C.c_int),
                 ("mu_init", C.c_double), ("bound_relax_factor", C.c_double), ("bound_push", C.c_double),
                 ("infinity", C.c_double), ("device", C.c_int), ("threads_per_instance", C.c_int),
-                ("ctas_per_sm", C.c_int), ("teams_per_cta", C.c_int), ("lockstep_groups", C.c_int)]
+                ("ctas_per_sm", C.c_int), ("teams_per_cta", C.c_int), ("lockstep_groups", C.c_int),
+                ("mu_strategy", C.c_int)]
 
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 _lib = None
+
+# cmpc_config.mu_strategy (include/cmpc_b200.h)
+MU_DEFAULT, MU_MONOTONE, MU_MEHROTRA = 0, 1, 2
 
 
 def load_library() -> C.CDLL:

@@ -46,6 +46,7 @@ struct Config {
     double bound_relax;  // bound_relax_factor
     double bound_push;   // bound_push = bound_frac
     double inf_bound;    // nlp_upper_bound_inf
+    int pc;              // 1: Mehrotra predictor-corrector barrier update, 0: IPOPT's monotone update (mu_strategy)
 };
 
 struct Instance {  // CasADi order, read only

@@ -16,6 +16,9 @@
 #pragma once
 
 #include "cmpc_warp.cuh"
+#if defined(CMPC_TRACE) && !defined(__CUDA_ARCH__)
+#include <cstdio>
+#endif
 
 namespace cmpc {
 
@@ -44,6 +47,7 @@ namespace cmpc {
 #define CMPC_ENTRY CMPC_FN
 #endif
 
+constexpr int PC_MAX_ITER = 50;  // predictor-corrector iterations after which an instance is handed to the monotone path
 constexpr int PS = 40;  // stride of a knot in the path-row arrays: friction 0..31 (16 c + 4 j + r) | step box 32..37 (32 + 3 c + q) | pad
 // per-knot table of constants
 constexpr int TS = 100;
@@ -54,7 +58,7 @@ constexpr int AWS = 32;  // stride of the per-knot values of the off-diagonal no
 struct WorkS {
     double *z, *dz, *zt, *gr, *res;                                                   // (N + 1) * ZS
     double *lam, *dlam, *ceq, *lamn, *vco, *beq;                                      // (N + 1) * ES
-    double *gp, *sl, *slt, *zl, *zu, *lo, *up, *yp, *ypn, *sig, *tt, *dsl, *dzl, *dzu, *dyp;  // N * PS
+    double *gp, *sl, *slt, *zl, *zu, *lo, *up, *yp, *ypn, *sig, *tt, *dsl, *dzl, *dzu, *dyp, *ccl, *ccu;  // N * PS
     double *tab;                                                                      // (N + 1) * TS
     double *sd, *aw, *dfc;                                                            // N * SD_STRIDE, N * AWS, N * 8
     double *small;                                                                    // (N + 1) * SMALL_STRIDE
@@ -62,7 +66,7 @@ struct WorkS {
 };
 CMPC_HD int works_doubles(int N)
 {
-    return 5 * (N + 1) * ZS + 6 * (N + 1) * ES + 15 * N * PS + (N + 1) * TS + N * (SD_STRIDE + AWS + 8) + (N + 1) * SMALL_STRIDE
+    return 5 * (N + 1) * ZS + 6 * (N + 1) * ES + 17 * N * PS + (N + 1) * TS + N * (SD_STRIDE + AWS + 8) + (N + 1) * SMALL_STRIDE
            + N * WRIC_STRIDE;
 }
 CMPC_HD void works_carve(double* base, int N, WorkS& w)
@@ -73,7 +77,7 @@ CMPC_HD void works_carve(double* base, int N, WorkS& w)
     w.lam = c; c += ne; w.dlam = c; c += ne; w.ceq = c; c += ne; w.lamn = c; c += ne; w.vco = c; c += ne; w.beq = c; c += ne;
     w.gp = c; c += np; w.sl = c; c += np; w.slt = c; c += np; w.zl = c; c += np; w.zu = c; c += np; w.lo = c; c += np;
     w.up = c; c += np; w.yp = c; c += np; w.ypn = c; c += np; w.sig = c; c += np; w.tt = c; c += np; w.dsl = c; c += np;
-    w.dzl = c; c += np; w.dzu = c; c += np; w.dyp = c; c += np;
+    w.dzl = c; c += np; w.dzu = c; c += np; w.dyp = c; c += np; w.ccl = c; c += np; w.ccu = c; c += np;
     w.tab = c; c += (N + 1) * TS;
     w.sd = c; c += N * SD_STRIDE; w.aw = c; c += N * AWS; w.dfc = c; c += N * 8;
     w.small = c; c += (N + 1) * SMALL_STRIDE;
@@ -85,7 +89,10 @@ struct KktStats {
     double sum_y, sum_z, nb, nrows;   // for the scaling factors s_d, s_c
 };
 struct StepStats { double rho, amax, az, dphi, bad; };
-struct EvalStats { double f, theta, phi; };
+struct EvalStats { double f, theta, bar; };  // objective, l1 infeasibility, barrier sum (phi_mu = f + mu * bar)
+// affine-scaling (predictor) step: 1 / step length to the boundary (primal, dual), the coefficients of the mean
+// complementarity after the step  (s00 + ap s10 + ad s01 + ap ad s11) / nb
+
 
 // shared memory of one team: the Riccati block first (P at offset 0: 16-byte aligned async copies), then everything the
 // interior-point loop would otherwise keep on the thread stacks.  Local memory is poison here: the shared-memory carve-out
@@ -225,7 +232,7 @@ CMPC_ENTRY double hess_dz_entry(const Config& cfg, const WorkS& w, double dw, in
 // ------------------------------------------------------------------------------------------------ evaluation of a point
 // stage data, equality residuals, path row values, objective, theta (l1 infeasibility) and the barrier function at (zsrc, slsrc)
 template <int NT, int G, class Cta>
-CMPC_FN void eval_point(Team T, Cta& cta, const Config& cfg, ISmem& sm, const double* zsrc, const double* slsrc, double mu)
+CMPC_FN void eval_point(Team T, Cta& cta, const Config& cfg, ISmem& sm, const double* zsrc, const double* slsrc)
 {
     cta_align<G>(T);
     const WorkS& w = sm.w;
@@ -249,7 +256,7 @@ CMPC_FN void eval_point(Team T, Cta& cta, const Config& cfg, ISmem& sm, const do
             }
         }
     CMPC_LANES_END
-    double acc[3] = {0.0, 0.0, 0.0};  // f, theta, barrier terms
+    double acc[3] = {0.0, 0.0, 0.0};  // f, theta, barrier terms (without the factor mu)
     CMPC_LANES
         CMPC_ROLES(63) CMPC_KNOTS(0, N) {
             const double* t = w.tab + k * TS;
@@ -304,10 +311,10 @@ CMPC_FN void eval_point(Team T, Cta& cta, const Config& cfg, ISmem& sm, const do
                     else {
                         const double s = slsrc[pr];
                         acc[1] += fabs(g - s);
-                        if (hl) acc[2] -= mu * log(s - sl);
-                        if (hu) acc[2] -= mu * log(su - s);
-                        if (hl && !hu) acc[2] += KAPPA_D * mu * (s - sl);
-                        if (hu && !hl) acc[2] += KAPPA_D * mu * (su - s);
+                        if (hl) acc[2] -= log(s - sl);
+                        if (hu) acc[2] -= log(su - s);
+                        if (hl && !hu) acc[2] += KAPPA_D * (s - sl);
+                        if (hu && !hl) acc[2] += KAPPA_D * (su - s);
                     }
                 }
             } else if (k < N && r >= 54 && r < 60) {
@@ -330,7 +337,7 @@ CMPC_FN void eval_point(Team T, Cta& cta, const Config& cfg, ISmem& sm, const do
     CMPC_LANES_END_NOSYNC
     cta.template reduce3<0, 0, 3>(acc, acc, acc);
     CMPC_LANES
-        if (lane == 0) { sm.es.f = acc[0]; sm.es.theta = acc[1]; sm.es.phi = acc[0] + acc[2]; }
+        if (lane == 0) { sm.es.f = acc[0]; sm.es.theta = acc[1]; sm.es.bar = acc[2]; }
     CMPC_LANES_END
 }
 
@@ -490,7 +497,7 @@ CMPC_FN void barrier_pass(Team T, const Config& cfg, const WorkS& w, double mu, 
 // eliminated rows of the Newton system from dz (W-B eq. 13), then the multipliers of the equality rows by the adjoint
 // recursion  lambda+_k = A_k' lambda+_{k+1} - [grad f + W dz + sum_box a_i (y_i + dy_i)]_{s_k}  (exact for the given dz)
 template <int NT, int G>
-CMPC_FN void recover_pass(Team T, const Config& cfg, const WorkS& w, double mu, double dw, double dc)
+CMPC_FN void recover_pass(Team T, const Config& cfg, const WorkS& w, double mu, double dw, double dc, bool pc)
 {
     cta_align<G>(T);
     const int N = cfg.N;
@@ -509,8 +516,10 @@ CMPC_FN void recover_pass(Team T, const Config& cfg, const WorkS& w, double mu, 
                         const double s = w.sl[pr];
                         ds = jd + (w.gp[pr] - s);  // (g - s) first: jd can be below ulp(g)
                         double rs = -w.yp[pr];
-                        if (hl) { const double rd = 1.0 / (s - sl), zl = w.zl[pr]; rs -= mu * rd; dzl = mu * rd - zl - zl * rd * ds; }
-                        if (hu) { const double rd = 1.0 / (su - s), zu = w.zu[pr]; rs += mu * rd; dzu = mu * rd - zu + zu * rd * ds; }
+                        // complementarity targets: mu, or mu -+ ds_aff dz_aff (Mehrotra's second-order corrector)
+                        const double ml = pc ? mu - w.ccl[pr] : mu, mup = pc ? mu + w.ccu[pr] : mu;
+                        if (hl) { const double rd = 1.0 / (s - sl), zl = w.zl[pr]; rs -= ml * rd; dzl = ml * rd - zl - zl * rd * ds; }
+                        if (hu) { const double rd = 1.0 / (su - s), zu = w.zu[pr]; rs += mup * rd; dzu = mup * rd - zu + zu * rd * ds; }
                         if (hl && !hu) rs += KAPPA_D * mu;
                         if (hu && !hl) rs -= KAPPA_D * mu;
                         dy = w.sig[pr] * ds + rs;
@@ -566,6 +575,93 @@ CMPC_FN void recover_pass(Team T, const Config& cfg, const WorkS& w, double mu, 
         }
     }
     team_sync<NT, G>(T);
+}
+
+// predictor of the Mehrotra mode.  From the affine-scaling step dz (complementarity target 0): the slack / bound-multiplier
+// parts of the step, their products (the second-order terms), the step lengths to the boundary and the mean complementarity
+// after the step -> the new barrier parameter (returned in mu).  The corrector only changes the right hand side of the
+// Newton system: w.res receives  J_path' dt  with  dt = change of the barrier gradient terms for the complementarity targets
+// mu -+ ds_aff dz_aff , the right hand side of one refinement sweep (refine_backward + riccati_forward).
+template <int NT, int G, class Cta>
+CMPC_FN void affine_pass(Team T, Cta& cta, const Config& cfg, ISmem& sm, double mu_min, double& mu)
+{
+    cta_align<G>(T);
+    const WorkS& w = sm.w;
+    const int N = cfg.N;
+    double vmax[2] = {1.0, 1.0};                  // 1 / alpha_aff (primal), 1 / alpha_aff (dual)
+    double vsum[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // s00, s10, s01, s11, number of bounds
+    CMPC_LANES
+        CMPC_ROLES(38) CMPC_KNOTS(0, N - 1) {
+            const int pr = k * PS + r;
+            const double sl = w.lo[pr], su = w.up[pr];
+            const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
+            double cl = 0.0, cu = 0.0, rl = 0.0, ru = 0.0;
+            if ((hl || hu) && !(sl == su)) {
+                const double s = w.sl[pr];
+                const double ds = path_dot(w.tab + k * TS, w.dz + k * ZS, w.dz + (k + 1) * ZS, r, 0) + (w.gp[pr] - s);
+                if (hl) {
+                    const double d = s - sl, z = w.zl[pr];
+                    rl = 1.0 / d;
+                    const double q = ds * rl, dzv = -z - z * q;
+                    vmax[0] = fmax(vmax[0], -q); vmax[1] = fmax(vmax[1], 1.0 + q);
+                    vsum[0] += d * z; vsum[1] += ds * z; vsum[2] += d * dzv; vsum[3] += ds * dzv; vsum[4] += 1.0;
+                    cl = ds * dzv;
+                }
+                if (hu) {
+                    const double d = su - s, z = w.zu[pr];
+                    ru = 1.0 / d;
+                    const double q = ds * ru, dzv = -z + z * q;
+                    vmax[0] = fmax(vmax[0], q); vmax[1] = fmax(vmax[1], 1.0 - q);
+                    vsum[0] += d * z; vsum[1] -= ds * z; vsum[2] += d * dzv; vsum[3] -= ds * dzv; vsum[4] += 1.0;
+                    cu = ds * dzv;
+                }
+            }
+            w.ccl[pr] = cl; w.ccu[pr] = cu;
+            w.dzl[pr] = rl; w.dzu[pr] = ru;   // scratch until the recover pass: 1 / distance to the bound
+        }
+    CMPC_LANES_END_NOSYNC
+    cta.template reduce3<2, 0, 5>(vmax, vmax, vsum);
+    if (T.on && vsum[4] > 0.0 && vsum[0] > 0.0) {
+        // Mehrotra's rule: sigma = (mu_aff / mu_cur)^3, mu = sigma mu_cur
+        const double ap = 1.0 / vmax[0], ad = 1.0 / vmax[1];
+        const double aff = vsum[0] + ap * vsum[1] + ad * vsum[2] + ap * ad * vsum[3];
+        const double sg = fmin(1.0, fmax(0.0, aff / vsum[0]));
+        mu = fmax(mu_min, sg * sg * sg * vsum[0] / vsum[4]);
+    }
+    const double mun = mu;
+    CMPC_LANES
+        CMPC_ROLES(38) CMPC_KNOTS(0, N - 1) {
+            const int pr = k * PS + r;
+            const double rl = w.dzl[pr], ru = w.dzu[pr];
+            double dt = ru * (mun + w.ccu[pr]) - rl * (mun - w.ccl[pr]);
+            if (rl != 0.0 && ru == 0.0) dt += KAPPA_D * mun;
+            if (ru != 0.0 && rl == 0.0) dt -= KAPPA_D * mun;
+            w.dyp[pr] = dt;
+        }
+    CMPC_LANES_END
+    CMPC_LANES
+        CMPC_ROLES(NS + NU) CMPC_KNOTS(0, N) {
+            double v = 0.0;
+            if (r < NS) {
+                if (k > 0 && r >= 9) {
+                    const int c = (r - 9) / 3, a = (r - 9) % 3;
+                    const double* R = w.tab + (k - 1) * TS + T_R + 9 * c;
+                    const double* tb = w.dyp + (k - 1) * PS + 32 + 3 * c;
+                    v = R[a] * tb[0] + R[3 + a] * tb[1] + R[6 + a] * tb[2];
+                }
+            } else {
+                if (k == N) continue;
+                const int u = r - NS;
+                if (u >= 6) {
+                    const int f = u - 6, c = f / 12, j = (f % 12) / 3, a = f % 3;
+                    const double* ar = w.tab + k * TS + T_AR + 12 * c + a;  // row q at ar[3 q]
+                    const double* tf = w.dyp + k * PS + 16 * c + 4 * j;
+                    v = ar[0] * tf[0] + ar[3] * tf[1] + ar[6] * tf[2] + ar[9] * tf[3];
+                }
+            }
+            w.res[k * ZS + r] = v;
+        }
+    CMPC_LANES_END
 }
 
 // residual of the linearised stationarity (right hand side of the refinement) and, for the line search, the fraction to the
@@ -656,8 +752,10 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
     double* x_io = nullptr;
     double* lam_io = nullptr;
     bool warm = false;
-    double mu = cfg.mu_init, tau = TAU_MIN, f = 0, theta0 = 0, phi0 = 0, theta_max = 0, theta_min = 0, dw_last = 0, E0 = 0;
-    int nfilt = 0, it = 0;
+    double mu = cfg.mu_init, tau = TAU_MIN, f = 0, theta0 = 0, bar0 = 0, theta_max = 0, theta_min = 0, dw_last = 0, E0 = 0;
+    int nfilt = 0, it = 0, it_base = 0;
+    bool pc = cfg.pc != 0;   // Mehrotra predictor-corrector barrier update (false: IPOPT's monotone update)
+    bool redo = false;       // the predictor-corrector run of the instance failed: solve it again on the monotone path
 
     for (;;) {
         // ---- work queue: a team without an instance takes the next one
@@ -676,8 +774,9 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
         if (want) {
             inst = ism.inst;
             if (inst >= batch) { alive = false; inst = -1; }
-            else fresh = true;
+            else { fresh = true; pc = cfg.pc != 0; it_base = 0; }
         }
+        if (redo) { fresh = true; redo = false; }
         if (!vote_any<G>(T, alive)) break;
         int fin = -1;  // >= 0: the instance is finished with this status at the end of the round
 
@@ -761,6 +860,7 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
             w.lo[pr] = lo; w.up[pr] = up; w.yp[pr] = y;
             w.sl[pr] = 0.0; w.zl[pr] = 0.0; w.zu[pr] = 0.0; w.gp[pr] = 0.0; w.sig[pr] = 0.0; w.tt[pr] = 0.0;
             w.dsl[pr] = 0.0; w.dzl[pr] = 0.0; w.dzu[pr] = 0.0; w.dyp[pr] = 0.0; w.ypn[pr] = 0.0; w.slt[pr] = 0.0;
+            w.ccl[pr] = 0.0; w.ccu[pr] = 0.0;
         }
     CMPC_LANES_END_NOSYNC
             cta.template maxv<1>(bad);
@@ -769,7 +869,7 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
             // initial point: slacks pushed inside their bounds (bound_push / bound_frac), bound multipliers 1
             T.on = fresh;
             if (fresh) { mu = cfg.mu_init; tau = fmax(TAU_MIN, 1.0 - mu); nfilt = 0; dw_last = 0.0; it = 0; }
-            eval_point<NT, G>(T, cta, cfg, ism, w.z, w.sl, mu);  // path row values (the slacks are not set yet)
+            eval_point<NT, G>(T, cta, cfg, ism, w.z, w.sl);  // path row values (the slacks are not set yet)
     CMPC_LANES
         for (int it = lane; it < N * 64; it += NT) {
             const int k = it >> 6, l = it & 63;
@@ -796,9 +896,9 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
             w.zl[pr] = zl; w.zu[pr] = zu;
         }
     CMPC_LANES_END
-            eval_point<NT, G>(T, cta, cfg, ism, w.z, w.sl, mu);
+            eval_point<NT, G>(T, cta, cfg, ism, w.z, w.sl);
             if (fresh) {
-                f = ism.es.f; theta0 = ism.es.theta; phi0 = ism.es.phi;
+                f = ism.es.f; theta0 = ism.es.theta; bar0 = ism.es.bar;
                 theta_max = 1e4 * fmax(1.0, theta0); theta_min = 1e-4 * fmax(1.0, theta0);
             }
         }
@@ -810,20 +910,18 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
         kkt_pass<NT, G>(T, cta, cfg, ism);
         CMPC_TOC(1)
         KktStats ks = ism.ks;
-        bool mu_changed = false;
         if (act) {
             double cmp0;
             E0 = kkt_E(ks, 0.0, &cmp0);
             if (E0 <= cfg.tol && ks.dual <= 1.0 && ks.viol <= 1e-4 && cmp0 <= 1e-4) { fin = 0; act = false; }
-            else if (it == cfg.max_iter) { fin = 1; act = false; }
+            else if (it == cfg.max_iter || (pc && it == PC_MAX_ITER)) { fin = 1; act = false; }
         }
-        if (act) {
+        if (act && !pc) {
             // barrier update (eq. 7), filter reset
             while (kkt_E(ks, mu, nullptr) <= KAPPA_EPS * mu && mu > mu_min) {
                 mu = fmax(mu_min, fmin(KAPPA_MU * mu, mu * sqrt(mu)));
                 tau = fmax(TAU_MIN, 1.0 - mu);
                 nfilt = 0;
-                mu_changed = true;
             }
         }
         // ---- search direction with inertia correction (alg. IC): Cholesky failure inside the Riccati sweep <=> wrong inertia
@@ -833,7 +931,7 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
         bool needf = act;
         while (vote_any<G>(T, needf)) {
             T.on = needf;
-            barrier_pass<NT, G>(T, cfg, w, mu, dw, dc);
+            barrier_pass<NT, G>(T, cfg, w, pc ? 0.0 : mu, dw, dc);  // predictor-corrector: affine-scaling step first
             CMPC_TOC(2)
             const int rc = riccati_backward<NT, G>(T, cfg, io, sm, dw);
             CMPC_TOC(3)
@@ -850,7 +948,23 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
         T.on = act;
         riccati_forward<NT, G>(T, cfg, io, sm, false);
         CMPC_TOC(4)
-        recover_pass<NT, G>(T, cfg, w, mu, dw, dc);
+        // ---- Mehrotra's rule: barrier parameter from the affine-scaling step, then the corrector: same matrix, new right hand
+        //      side (complementarity targets mu -+ ds_aff dz_aff) = one refinement sweep whose result is accumulated into dz
+        {
+            const bool pcact = act && pc;
+            if (vote_any<G>(T, pcact)) {
+                T.on = pcact;
+                affine_pass<NT, G>(T, cta, cfg, ism, mu_min, mu);
+                if (pcact) { tau = fmax(TAU_MIN, 1.0 - mu); nfilt = 0; }
+                CMPC_TOC(5)
+                refine_backward<NT, G>(T, cfg, io, sm);
+                CMPC_TOC(15)
+                riccati_forward<NT, G>(T, cfg, io, sm, true);
+                CMPC_TOC(4)
+                T.on = act;
+            }
+        }
+        recover_pass<NT, G>(T, cfg, w, mu, dw, dc, pc);
         CMPC_TOC(5)
         step_pass<NT, G>(T, cta, cfg, ism, mu, dw, tau);
         StepStats ss = ism.ss;
@@ -865,7 +979,7 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
             if (needr) rho_prev = ss.rho;
             refine_backward<NT, G>(T, cfg, io, sm);
             riccati_forward<NT, G>(T, cfg, io, sm, true);
-            recover_pass<NT, G>(T, cfg, w, mu, dw, dc);
+            recover_pass<NT, G>(T, cfg, w, mu, dw, dc, pc);
             step_pass<NT, G>(T, cta, cfg, ism, mu, dw, tau);
             if (needr) { ss = ism.ss; ++rf; }
         }
@@ -873,22 +987,14 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
         if (act && ss.bad != 0.0) { fin = 3; act = false; }
         const double amax = ss.amax, az = ss.az, dphi = ss.dphi;
         // ---- filter line search (alg. A)
-        double theta = theta0, phi = phi0;
-        {
-            const bool need_eval = act && mu_changed;   // barrier function of the current point for the new mu
-            if (vote_any<G>(T, need_eval)) {
-                T.on = need_eval;
-                eval_point<NT, G>(T, cta, cfg, ism, w.z, w.sl, mu);
-                if (need_eval) { theta = ism.es.theta; phi = ism.es.phi; }
-            }
-        }
+        const double theta = theta0, phi = f + mu * bar0;  // barrier function of the current point for the current mu
         double amin;
         if (dphi < 0) {
             amin = fmin(GAMMA_THETA, GAMMA_PHI * theta / (-dphi));
             if (theta <= theta_min) amin = fmin(amin, DELTA_SW * pow(theta, S_THETA) / pow(-dphi, S_PHI));
         } else amin = GAMMA_THETA;
         amin *= GAMMA_ALPHA;
-        double alpha = amax, ft = f, th_t = theta, ph_t = phi;
+        double alpha = amax, ft = f, th_t = theta, ph_t = phi, bar_t = bar0;
         int accepted = 0, armijo = 0;
         bool pend = act;
         while (vote_any<G>(T, pend)) {
@@ -903,9 +1009,9 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
                     for (int i = lane; i < N * PS; i += NT) slt[i] = sl[i] + alpha * dsl[i];
                 }
             CMPC_LANES_END
-            eval_point<NT, G>(T, cta, cfg, ism, w.zt, w.slt, mu);
+            eval_point<NT, G>(T, cta, cfg, ism, w.zt, w.slt);
             if (pend) {
-                ft = ism.es.f; th_t = ism.es.theta; ph_t = ism.es.phi;
+                ft = ism.es.f; th_t = ism.es.theta; bar_t = ism.es.bar; ph_t = ft + mu * bar_t;
                 bool ok = (fabs(ph_t) < HUGE_VAL) && (fabs(th_t) < HUGE_VAL) && th_t <= theta_max;
                 for (int q = 0; ok && q < nfilt; ++q)
                     if (th_t >= filt_t[q] && ph_t >= filt_p[q]) ok = false;
@@ -937,7 +1043,7 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
         CMPC_LANES_END
         if (act) {
             if (!armijo && nfilt < MAX_FILTER) nfilt++;
-            f = ft; theta0 = th_t; phi0 = ph_t;
+            f = ft; theta0 = th_t; bar0 = bar_t;
         }
         CMPC_LANES
             {
@@ -961,7 +1067,12 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
             for (int i = lane; i < (N + 1) * ES; i += NT) w.lam[i] += alpha * w.dlam[i];
         CMPC_LANES_END
         CMPC_TOC(9)
+#if defined(CMPC_TRACE) && !defined(__CUDA_ARCH__)
+        if (act) printf("it %3d f %.10e E0 %.2e (d %.2e v %.2e) mu %.2e dw %.1e alpha %.3e az %.3e rho %.1e rf %d pc %d\n", it, f, E0, ks.dual, ks.viol, mu, dw, alpha, az, ss.rho, rf, (int)pc);
+#endif
         if (act) ++it;
+        // an instance the predictor-corrector path cannot finish starts again from its initial point on the monotone path
+        if (pc && fin >= 1 && fin <= 3) { pc = false; redo = true; it_base += it; fin = -1; }
 
         // ---- write-back of the instances that finished in this round (solution to the CasADi order), then back to the queue
         const bool done = fin >= 0;
@@ -987,7 +1098,7 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
                 if (T.lane == 0) {
                     if (obj_all) obj_all[inst] = f;
                     if (status_all) status_all[inst] = fin;
-                    if (iters_all) iters_all[inst] = it;
+                    if (iters_all) iters_all[inst] = it_base + it;
                 }
                 inst = -1;
             }

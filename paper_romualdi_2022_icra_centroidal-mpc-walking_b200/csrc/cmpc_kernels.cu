@@ -436,6 +436,7 @@ int cmpc_default_config(cmpc_config* c)
     for (int k = 0; k < 2; ++k) memcpy(c->corners[k], cr, sizeof cr);
     c->ipopt_tolerance = 1e-8; c->ipopt_max_iteration = 200; c->mu_init = 0.1; c->bound_relax_factor = 1e-8;
     c->bound_push = 0.01; c->infinity = 1e19; c->device = 0; c->threads_per_instance = 0; c->ctas_per_sm = 0;
+    c->mu_strategy = CMPC_MU_DEFAULT;
     return CMPC_OK;
 }
 
@@ -500,6 +501,8 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
     c.bound_relax = u->bound_relax_factor >= 0 ? u->bound_relax_factor : 1e-8;
     c.bound_push = u->bound_push > 0 ? u->bound_push : 0.01;
     c.inf_bound = u->infinity > 0 ? u->infinity : 1e19;
+    if (u->mu_strategy < 0 || u->mu_strategy > CMPC_MU_MEHROTRA) { delete h; return CMPC_E_INVALID; }
+    c.pc = u->mu_strategy == CMPC_MU_MONOTONE ? 0 : 1;
     h->device = u->device;
     cudaError_t e = cudaSetDevice(h->device);
     cudaDeviceProp prop;

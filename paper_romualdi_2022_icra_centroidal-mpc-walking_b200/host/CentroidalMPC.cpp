@@ -167,6 +167,14 @@ bool CentroidalMPC::Impl::loadParameters(const ParametersHandler::IParametersHan
     h.getParameter("is_warm_start_enabled", warmStartEnabled);
     h.getParameter("step_adjustment_enabled", stepAdjustmentEnabled);  // addition: false = every step box has zero width
     h.getParameter("cuda_device", cfg.device);                         // addition
+    {   // addition: barrier update of the batched interior point ("mehrotra" = library default, "monotone" = IPOPT's own path)
+        std::string muStrategy;
+        if (h.getParameter("mu_strategy", muStrategy)) {
+            if (muStrategy == "monotone") cfg.mu_strategy = CMPC_MU_MONOTONE;
+            else if (muStrategy == "mehrotra") cfg.mu_strategy = CMPC_MU_MEHROTRA;
+            else return fail("mu_strategy must be \"monotone\" or \"mehrotra\"");
+        }
+    }
 
     contacts.clear();
     for (int i = 0; i < maxContacts; ++i) {

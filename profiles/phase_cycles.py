@@ -11,7 +11,8 @@ wl = importlib.import_module(PKG + ".workloads")
 import torch
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 team = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-cfg = pkg.icub3_config(); cfg.threads_per_instance = team
+strategy = os.environ.get("CMPC_MU", "mehrotra")
+cfg = pkg.icub3_config(mu_strategy=pkg.MU_MEHROTRA if strategy == "mehrotra" else pkg.MU_MONOTONE); cfg.threads_per_instance = team
 s = pkg.BatchedCentroidalMPC(cfg)
 w = wl.walk_batch(N=15, dT=0.1, B=B, seed=0, state_noise=1.0, step_adjust=False)
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
@@ -23,11 +24,11 @@ for rep in range(3):
     obj, st, it, _ = s.solve(p, lb, ub, x)
     torch.cuda.synchronize()
 s.lib.cmpc_debug_profile(out)
-names = ["setup", "kkt_pass", "barrier_pass", "backward", "forward", "recover", "step", "refine", "line search", "accept",
-         "  bw: F1 load", "  bw: F2 form", "  bw: F3 form", "  bw: factor", "  bw: syrk+store"]
-v = np.array(out[:10], dtype=np.float64)
+names = ["setup", "kkt_pass", "barrier_pass", "backward", "forward (x2 with corrector)", "recover (+ affine pass)", "step", "refine", "line search", "accept",
+         "corrector backward sweep", "  bw: F1 load", "  bw: F2 form", "  bw: F3 form", "  bw: factor", "  bw: syrk+store"]
+v = np.array(list(out[:10]) + [out[15]], dtype=np.float64)
 vb = np.array(out[10:15], dtype=np.float64)
 iters = float(it.sum().item())
-print(f"batch {B} team {team or 'default'} iterations {iters:.0f}  total cycles/iteration {v.sum()/iters:.0f}")
+print(f"strategy {strategy} batch {B} team {team or 'default'} iterations {iters:.0f}  total cycles/iteration {v.sum()/iters:.0f}")
 for n, c in zip(names, list(v) + list(vb)):
-    print(f"{n:16s} {c/iters:12.0f} cycles/iteration  {100*c/v.sum():5.1f} %")
+    print(f"{n:28s} {c/iters:12.0f} cycles/iteration  {100*c/v.sum():5.1f} %")

@@ -22,7 +22,7 @@ class DevConfig(C.Structure):
     _fields_ = [("N", C.c_int), ("dT", C.c_double), ("w_com", C.c_double * 3), ("w_h", C.c_double), ("w_pos", C.c_double),
                 ("w_sym", C.c_double), ("w_rate", C.c_double * 3), ("corner", C.c_double * 24), ("fricA", C.c_double * 12),
                 ("tol", C.c_double), ("max_iter", C.c_int), ("mu_init", C.c_double), ("bound_relax", C.c_double),
-                ("bound_push", C.c_double), ("inf_bound", C.c_double)]
+                ("bound_push", C.c_double), ("inf_bound", C.c_double), ("pc", C.c_int)]
 
 
 @pytest.fixture(scope="module")
@@ -37,7 +37,7 @@ def hostsim():
     return L
 
 
-def dev_config(N, tol=1e-8, **kw):
+def dev_config(N, tol=1e-8, pc=0, **kw):
     o = make_cfg(N=N, **kw)   # oracle config: same fields (weights, corners, friction matrix)
     c = DevConfig()
     c.N, c.dT = N, o.dT
@@ -48,6 +48,7 @@ def dev_config(N, tol=1e-8, **kw):
     from oracle.oracle import Oracle
     c.fricA[:] = np.asarray(Oracle().friction_matrix(o.mu), dtype=np.float64).reshape(-1).tolist()
     c.tol, c.max_iter, c.mu_init, c.bound_relax, c.bound_push, c.inf_bound = tol, 200, 0.1, 1e-8, 0.01, 1e19
+    c.pc = pc
     return c, o
 
 
@@ -68,10 +69,13 @@ def run(L, fn, c, w, b):
               corners=[[(0.08, 0.03, 0), (0.08, -0.03, 0), (-0.08, -0.03, 0), (-0.08, 0.03, 0)]] * 2),
      dict(state_noise=1.0, step_adjust=False)),
 ])
-def test_hostsim_matches_oracle(hostsim, oracle, workloads, fn, N, kw, wkw):
-    c, o = dev_config(N, **kw)
+@pytest.mark.parametrize("pc", [0, 1], ids=["monotone", "mehrotra"])
+def test_hostsim_matches_oracle(hostsim, oracle, workloads, fn, N, kw, wkw, pc):
+    if fn == "hostsim_solve" and pc:
+        pytest.skip("the generic one-thread solver of cmpc_core.cuh has the monotone update only")
+    c, o = dev_config(N, pc=pc, **kw)
     w = workloads.walk_batch(N=N, B=3, seed=5, **wkw)
-    xo, lo, st = oracle.solve_batch(o, w["p"], w["lbg"], w["ubg"], w["x0"], threads=3)
+    xo, lo, st = oracle.solve_batch(o, w["p"], w["lbg"], w["ubg"], w["x0"], threads=3, opts=oracle.default_opts(mehrotra=pc))
     for b in range(3):
         status, it, obj, x, lam = run(hostsim, fn, c, w, b)
         assert status == 0 and st[b].status == 0
