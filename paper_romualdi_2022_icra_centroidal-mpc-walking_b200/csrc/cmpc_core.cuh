@@ -124,7 +124,10 @@ constexpr double DW_FIRST = 1e-4, DW_MIN = 1e-20, DW_MAX = 1e40, KW_PLUS_FIRST =
 constexpr double DC_BAR = 1e-8, DC_FLOOR = 0.0;
 constexpr int MAX_FILTER = 16;
 constexpr int MAX_REFINE = 2;          // iterative refinement steps of the Newton system (IPOPT: max_refinement_steps 10)
-constexpr double REFINE_TOL = 1e-10;   // absolute stationarity residual of the linear system that triggers a step
+#ifndef CMPC_REFINE_TOL
+#define CMPC_REFINE_TOL 1e-9   // a factor 10 below the default KKT tolerance (1e-10: same iterations, 4 % slower)
+#endif
+constexpr double REFINE_TOL = CMPC_REFINE_TOL;   // absolute stationarity residual of the linear system that triggers a step
 constexpr double GRAV_Z = -9.80665;  // tmp.c:3916
 
 // ------------------------------------------------------------------------------------------------ small helpers

@@ -744,6 +744,7 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
     double* filt_t = ism.filt_t;
     double* filt_p = ism.filt_p;
     const double mu_min = cfg.tol / (KAPPA_EPS + 1.0);
+    const double refine_tol = fmin(REFINE_TOL, 0.1 * cfg.tol);  // residual of the linear system that triggers a refinement sweep
 
     // state of the instance the team is working on (thread-private copies, uniform over the team)
     bool alive = true;   // the queue still has work for this team
@@ -973,7 +974,7 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
         double rho_prev = HUGE_VAL;
         int rf = 0;
         for (;;) {
-            const bool needr = act && rf < MAX_REFINE && ss.rho > REFINE_TOL && !(ss.rho > 0.5 * rho_prev);
+            const bool needr = act && rf < MAX_REFINE && ss.rho > refine_tol && !(ss.rho > 0.5 * rho_prev);
             if (!vote_any<G>(T, needr)) break;
             T.on = needr;
             if (needr) rho_prev = ss.rho;

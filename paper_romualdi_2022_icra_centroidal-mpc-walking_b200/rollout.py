@@ -22,8 +22,10 @@ PUSH_THRESHOLD = 0.7  # WholeBodyQPBlock.cpp:1018
 
 
 def closed_loop_rollout(solver: BatchedCentroidalMPC, B: int, ticks: int, seed: int = 0, dT: float = 0.1, wbc_dt: float = 0.002,
-                        push_prob: float = 1.0, push_range=(1.0, 3.0), step_adjust: bool = True, yaw_range: float = 0.0):
-    """returns dict of per-instance numpy arrays: converged ticks, iterations, max CoM tracking error, min CoM height"""
+                        push_prob: float = 1.0, push_range=(1.0, 3.0), step_adjust: bool = True, yaw_range: float = 0.0,
+                        time_device: bool = False):
+    """returns dict of per-instance numpy arrays: converged ticks, iterations, max CoM tracking error, min CoM height;
+    time_device = True adds "device_ms": CUDA-event time of the kernels of every tick (shift + solve + plant)"""
     N, dev = solver.N, solver.device
     L = Layout(N)
     rng = np.random.default_rng(seed)
@@ -44,6 +46,7 @@ def closed_loop_rollout(solver: BatchedCentroidalMPC, B: int, ticks: int, seed: 
     err_max = np.zeros(B)
     zmin = np.full(B, np.inf)
     g0 = L.p_glob()
+    events = []
     for t in range(ticks):
         w = walk_batch(N=N, dT=dT, B=B, seed=seed, phase=phase0 + t, step_adjust=step_adjust, yaw_range=yaw_range)
         p, lbg, ubg = tens(w["p"]), tens(w["lbg"]), tens(w["ubg"])
@@ -57,7 +60,13 @@ def closed_loop_rollout(solver: BatchedCentroidalMPC, B: int, ticks: int, seed: 
             d_lam = torch.zeros(B, L.m, dtype=torch.float64, device=dev)
             warm = False
         else:
+            if time_device:
+                ev_shift = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev_shift[0].record()
             solver.shift_warmstart(d_x, d_lam)
+            if time_device:
+                ev_shift[1].record()
+                events.append(ev_shift)
             warm = True
         # feedback: plant state, actual footsteps instead of planned ones, external force at knot 0
         p[:, g0:g0 + 9] = state
@@ -72,11 +81,17 @@ def closed_loop_rollout(solver: BatchedCentroidalMPC, B: int, ticks: int, seed: 
             p[:, L.p_cur(c):L.p_cur(c) + 3] = foot[:, c]
             lbg[:, 9 + 3 * c:12 + 3 * c] = foot[:, c]
             ubg[:, 9 + 3 * c:12 + 3 * c] = foot[:, c]
+        if time_device:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         obj, status, iters, _ = solver.solve(p, lbg, ubg, d_x, d_lam, warm_duals=warm)
         # plant: RK4 under the knot-0 forces (+ the push), then the next tick's foot positions from the MPC's own plan
         ext6 = torch.zeros(B, 6, dtype=torch.float64, device=dev)
         ext6[:, :3] = tens(ext)
         solver.rollout_plant(d_x, p, state, wbc_dt, substeps, ext=ext6)
+        if time_device:
+            ev[1].record()
+            events.append(ev)
         for c in range(2):
             foot[:, c] = d_x[:, L.x_pos(c, 1):L.x_pos(c, 1) + 3]
         st = status.cpu().numpy()
@@ -86,4 +101,8 @@ def closed_loop_rollout(solver: BatchedCentroidalMPC, B: int, ticks: int, seed: 
         ref = w["comref"][:, 1]                                   # the reference of the knot the plant has just reached
         err_max = np.maximum(err_max, np.linalg.norm(com[:, :2] - ref[:, :2], axis=1))
         zmin = np.minimum(zmin, com[:, 2])
-    return dict(converged_ticks=conv, iterations=iters_sum, com_err_max=err_max, com_z_min=zmin, push_tick=push_tick, ticks=ticks)
+    out = dict(converged_ticks=conv, iterations=iters_sum, com_err_max=err_max, com_z_min=zmin, push_tick=push_tick, ticks=ticks)
+    if time_device:
+        torch.cuda.synchronize()
+        out["device_ms"] = float(sum(a.elapsed_time(b) for a, b in events))
+    return out

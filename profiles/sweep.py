@@ -37,5 +37,5 @@ print(f"{'N':>4} {'batch':>8} {'ms':>10} {'solves/s':>12} {'converged':>10} {'me
 for N in (10, 12, 15, 20, 25, 30, 40, 50):
     print("{:4d} {:8d} {:10.2f} {:12.0f} {:10d} {:11.2f}".format(*run(N, 1036)), flush=True)
 print("batch sweep (N = 12)")
-for B in (1, 8, 64, 512, 4096, 32768):
+for B in (1, 8, 64, 512, 4096, 32768, 262144):
     print("{:4d} {:8d} {:10.2f} {:12.0f} {:10d} {:11.2f}".format(*run(12, B, reps=2)), flush=True)
