@@ -106,7 +106,28 @@ def cpu_oracle_rate(ocfg, w, sample: int, threads: int, tol: float):
     dt = time.perf_counter() - t0
     ok = sum(1 for s in st if s.status == 0)
     its = float(np.mean([s.iters for s in st]))
+    cpu_oracle_rate.last = (x, np.array([s.obj for s in st]), np.array([s.status for s in st]))   # for the parity report
     return sample / dt, dt, ok, its
+
+
+def parity_report(x_gpu, obj_gpu, status_gpu, L):
+    """north_star: "the fraction of instances landing in the same local optimum is reported" -- GPU solutions of the timed
+    workload (default barrier update) against the oracle's solutions of the same instances (IPOPT's default path)."""
+    xo, obj_o, st_o = cpu_oracle_rate.last
+    n, N = xo.shape[0], L.N
+    both = (st_o == 0) & (status_gpu[:n] == 0)
+    rel = lambda a, b: np.max(np.abs(a - b), axis=1) / np.maximum(1.0, np.max(np.abs(b), axis=1))  # noqa: E731
+    st = np.arange(0, 9 * (N + 1))                                # com, dcom, h trajectories
+    fs = np.concatenate([np.arange(L.x_pos(c, 0), L.x_pos(c, 0) + 3 * (N + 1)) for c in range(2)])   # footsteps
+    frc = np.concatenate([np.arange(L.x_frc(c, 0, 0), L.x_frc(c, 0, 0) + 12 * N) for c in range(2)])  # corner forces
+    xg = x_gpu[:n]
+    d_obj = np.abs(obj_gpu[:n] - obj_o) / np.maximum(1.0, np.abs(obj_o))
+    same_state = both & (d_obj <= 1e-6) & (rel(xg[:, st], xo[:, st]) <= 1e-5) & (rel(xg[:, fs], xo[:, fs]) <= 1e-5)
+    same_all = same_state & (rel(xg[:, frc], xo[:, frc]) <= 1e-5)
+    return {"instances": int(n), "both_converged": int(both.sum()),
+            "same_objective_trajectories_footsteps": int(same_state.sum()), "same_corner_forces_too": int(same_all.sum()),
+            "tolerances": "objective 1e-6 relative, scaled inf-norm 1e-5", "against": "oracle, IPOPT's default (monotone) path",
+            "max_rel_objective_difference": float(d_obj[both].max()) if both.any() else None}
 
 
 def run_reference(args):
@@ -354,6 +375,7 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": "solves/s", "cores": cores, "kind": "port",
                                     "sample": f"first {sample} instances of the workload, {dt:.1f} s, {ok}/{sample} "
                                               f"converged, mean {its:.1f} iterations (oracle = IPOPT restatement)"}
+            line["parity"] = parity_report(h_x.numpy(), h_obj.numpy(), h_st.numpy(), solver.L)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

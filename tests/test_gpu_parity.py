@@ -361,3 +361,41 @@ def test_predictor_corrector_lands_on_the_monotone_optimum(oracle, workloads, ro
         assert same_forces == 64
     assert iters.mean() < 0.8 * it_o
     s.close()
+
+
+def test_full_size_ergocub_shard_properties(oracle, workloads):
+    """BASELINE config 3, the shard of one GPU (65536 / 8 instances, step adjustment and friction cones active, state noise
+    x 2, yaw +-0.3): every instance converges in a bounded number of iterations on both barrier updates, the two land on
+    the same optimum (objective 1e-6, all variable groups 1e-5: unique optimum with the symmetry weight), and a sample
+    satisfies the KKT conditions evaluated with the ORACLE's functions."""
+    P = pkg()
+    B = 8192
+    w = workloads.walk_batch(N=12, B=B, seed=3, state_noise=2.0, yaw_range=0.3, step_adjust=True)
+    res = {}
+    for strat in STRATEGIES:
+        s = P.BatchedCentroidalMPC(P.ergocub_config(**strategy_kw(strat)))
+        res[strat] = s.solve_host(w["p"], w["lbg"], w["ubg"], w["x0"])
+        L = s.L
+        s.close()
+        x, lam, obj, status, iters = res[strat]
+        assert (status == 0).all(), (strat, np.bincount(status), np.where(status != 0)[0][:10])
+        assert iters.max() <= (25 if strat == "mehrotra" else 40), (strat, iters.max())
+    xm, lm, om_, _, itm = res["mehrotra"]
+    xq, lq, oq, _, itq = res["monotone"]
+    assert np.max(np.abs(om_ - oq) / np.maximum(1.0, np.abs(oq))) <= 1e-6
+    for name, idx in groups(L).items():
+        err = np.max(np.abs(xm[:, idx] - xq[:, idx]), axis=1) / np.maximum(1.0, np.max(np.abs(xq[:, idx]), axis=1))
+        assert err.max() <= 1e-5, (name, err.max(), int(err.argmax()))
+    assert itm.mean() < 0.75 * itq.mean()
+    cfg = make_cfg(w_pos=2000.0)
+    jc, jr = oracle.jac_sparsity(12)
+    for b in range(0, B, 512):
+        f, grad, g, jnz = oracle.jac_fg(cfg, xm[b], w["p"][b])
+        r = grad.copy()
+        for c in range(555):
+            sl = slice(jc[c], jc[c + 1])
+            r[c] += np.dot(jnz[sl], lm[b][jr[sl]])
+        scale = max(100.0, np.sum(np.abs(lm[b])) / 651) / 100.0
+        assert np.max(np.abs(r)) / scale < 1e-7, (b, np.max(np.abs(r)))
+        assert np.maximum(np.maximum(w["lbg"][b] - g, g - w["ubg"][b]), 0.0).max() < 4e-8
+        assert abs(f - om_[b]) <= 1e-10 * abs(f)
