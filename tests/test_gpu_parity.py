@@ -399,3 +399,24 @@ def test_full_size_ergocub_shard_properties(oracle, workloads):
         assert np.max(np.abs(r)) / scale < 1e-7, (b, np.max(np.abs(r)))
         assert np.maximum(np.maximum(w["lbg"][b] - g, g - w["ubg"][b]), 0.0).max() < 4e-8
         assert abs(f - om_[b]) <= 1e-10 * abs(f)
+
+
+def test_predictor_corrector_hands_hard_instances_to_the_monotone_path(oracle, workloads):
+    """4 x the nominal state noise: one instance of this batch defeats the predictor-corrector (line-search failure after six
+    iterations); it is solved again from its initial point on the monotone path inside the same launch -- same result and
+    (nearly) the same iteration total as the oracle, which does the same."""
+    P = pkg()
+    s = P.BatchedCentroidalMPC(P.ergocub_config())
+    w = workloads.walk_batch(N=12, B=96, seed=4, state_noise=4.0, yaw_range=0.3, step_adjust=True)
+    x, lam, obj, status, iters = s.solve_host(w["p"], w["lbg"], w["ubg"], w["x0"])
+    xo, lo, st = oracle.solve_batch(make_cfg(w_pos=2000.0), w["p"], w["lbg"], w["ubg"], w["x0"], threads=os.cpu_count() or 4,
+                                    opts=oracle.default_opts(mehrotra=1))
+    s.close()
+    assert (status == 0).all(), np.bincount(status)
+    fell_back = [b for b in range(96) if st[b].n_fallback]
+    assert fell_back, "the workload no longer contains an instance that needs the monotone path"
+    for b in range(96):
+        assert st[b].status == 0
+        assert abs(obj[b] - st[b].obj) <= 1e-6 * max(1.0, abs(st[b].obj)), (b, obj[b], st[b].obj)
+    for b in fell_back:
+        assert iters[b] > 25 and abs(int(iters[b]) - st[b].iters) <= 5, (b, iters[b], st[b].iters)
