@@ -495,7 +495,8 @@ static int ipm_core(const cmpc_oracle_nlp_fn* F, int N, const cmpc_oracle_ipm_op
         }
     }
     double mu = opts->mu_init, tau = fmax(TAU_MIN, 1.0 - mu);
-    const double mu_min = opts->tol / (KAPPA_EPS + 1.0);
+    /* IPOPT: the barrier parameter stops at min(tol, compl_inf_tol) / (barrier_tol_factor + 1), compl_inf_tol = 1e-4 */
+    const double mu_min = fmin(opts->tol, 1e-4) / (KAPPA_EPS + 1.0);
     double theta0 = infeas_l1(W, W->g, W->s);
     const double theta_max = 1e4 * fmax(1.0, theta0), theta_min = 1e-4 * fmax(1.0, theta0);
     double filt_t[MAX_FILTER], filt_p[MAX_FILTER]; int nfilt = 0;

@@ -1057,7 +1057,7 @@ CMPC_HD Result ipm_solve(Cta& cta, const Config& cfg, const Instance& in, const 
     cta.sync();
 
     double mu = cfg.mu_init, tau = fmax(TAU_MIN, 1.0 - mu);
-    const double mu_min = cfg.tol / (KAPPA_EPS + 1.0);
+    const double mu_min = fmin(cfg.tol, 1e-4) / (KAPPA_EPS + 1.0);  // IPOPT: min(tol, compl_inf_tol) / (barrier_tol_factor + 1)
     double theta0, phi0;
     theta_phi(cta, cfg, in, w, w.g, w.s, f, mu, theta0, phi0);
     const double theta_max = 1e4 * fmax(1.0, theta0), theta_min = 1e-4 * fmax(1.0, theta0);

@@ -743,7 +743,7 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
     CMPC_LANES_END
     double* filt_t = ism.filt_t;
     double* filt_p = ism.filt_p;
-    const double mu_min = cfg.tol / (KAPPA_EPS + 1.0);
+    const double mu_min = fmin(cfg.tol, 1e-4) / (KAPPA_EPS + 1.0);  // IPOPT: min(tol, compl_inf_tol) / (barrier_tol_factor + 1)
     const double refine_tol = fmin(REFINE_TOL, 0.1 * cfg.tol);  // residual of the linear system that triggers a refinement sweep
 
     // state of the instance the team is working on (thread-private copies, uniform over the team)

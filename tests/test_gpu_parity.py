@@ -420,3 +420,26 @@ def test_predictor_corrector_hands_hard_instances_to_the_monotone_path(oracle, w
         assert abs(obj[b] - st[b].obj) <= 1e-6 * max(1.0, abs(st[b].obj)), (b, obj[b], st[b].obj)
     for b in fell_back:
         assert iters[b] > 25 and abs(int(iters[b]) - st[b].iters) <= 5, (b, iters[b], st[b].iters)
+
+
+@pytest.mark.parametrize("strategy", STRATEGIES)
+@pytest.mark.parametrize("tol", [1e-2, 1e-4])
+def test_ini_tolerances(oracle, workloads, tol, strategy):
+    """ipopt_tolerance of the reference's ergoCub ini files: 1e-4 (ergoCubGazeboV1 / V1_1) and 1e-2 (ergoCubSN000 / SN001,
+    where IPOPT's constr_viol_tol / compl_inf_tol 1e-4 decide and the barrier parameter goes down to min(tol, 1e-4) / 11):
+    every instance converges, along the same path as the oracle (same iteration count within one, objective within 1e-6)
+    and to within the tolerance of the tight solution."""
+    P = pkg()
+    w = workloads.walk_batch(N=12, B=64, seed=9, state_noise=2.0, yaw_range=0.3)
+    s = P.BatchedCentroidalMPC(P.ergocub_config(ipopt_tolerance=tol, **strategy_kw(strategy)))
+    x, lam, obj, status, iters = s.solve_host(w["p"], w["lbg"], w["ubg"], w["x0"])
+    s.close()
+    xo, lo, st = oracle.solve_batch(make_cfg(w_pos=2000.0), w["p"], w["lbg"], w["ubg"], w["x0"], threads=os.cpu_count() or 4,
+                                    opts=oracle_opts(oracle, strategy, tol=tol))
+    xt, lt, stt = oracle.solve_batch(make_cfg(w_pos=2000.0), w["p"], w["lbg"], w["ubg"], w["x0"], threads=os.cpu_count() or 4)
+    assert (status == 0).all(), np.bincount(status)
+    for b in range(64):
+        assert st[b].status == 0
+        assert abs(int(iters[b]) - st[b].iters) <= 1, (b, iters[b], st[b].iters)
+        assert abs(obj[b] - st[b].obj) <= 1e-6 * max(1.0, abs(st[b].obj)), (b, obj[b], st[b].obj)
+        assert abs(obj[b] - stt[b].obj) <= 1e-3 * max(1.0, abs(stt[b].obj)), (b, obj[b], stt[b].obj)

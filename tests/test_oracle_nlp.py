@@ -126,3 +126,18 @@ def test_general_horizon_finite_differences(oracle):
                 Jm[jr[jc[cc]:jc[cc + 1]], cc] = jm[jc[cc]:jc[cc + 1]]
             hcol = (gradp - gradm) / (2 * eps) + ((Jp - Jm) / (2 * eps)).T @ lam
             assert np.max(np.abs(hcol - H[:, c])) < 1e-4 * max(1.0, np.max(np.abs(H[:, c])))
+
+
+@pytest.mark.parametrize("mehrotra", [0, 1])
+def test_oracle_ipm_converges_at_the_ini_tolerances(oracle, workloads, mehrotra):
+    """ipopt_tolerance 1e-2 (ergoCubSN000/SN001 ini) and 1e-4 (ergoCubGazeboV1_1 ini): the barrier parameter must go down to
+    min(tol, compl_inf_tol) / 11, otherwise compl_inf_tol = 1e-4 can never be met"""
+    from oracle.oracle import make_cfg
+    w = workloads.walk_batch(N=12, B=6, seed=2, state_noise=2.0, yaw_range=0.3)
+    tight = oracle.solve_batch(make_cfg(w_pos=2000.0), w["p"], w["lbg"], w["ubg"], w["x0"], threads=3)[2]
+    for tol in (1e-2, 1e-4):
+        x, lam, st = oracle.solve_batch(make_cfg(w_pos=2000.0), w["p"], w["lbg"], w["ubg"], w["x0"], threads=3,
+                                        opts=oracle.default_opts(tol=tol, mehrotra=mehrotra))
+        for b in range(6):
+            assert st[b].status == 0 and st[b].iters < tight[b].iters
+            assert abs(st[b].obj - tight[b].obj) <= 1e-3 * abs(tight[b].obj)
