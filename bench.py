@@ -34,12 +34,12 @@ PKG = "paper_romualdi_2022_icra_centroidal-mpc-walking_b200"
 # FP64 flop executed per interior-point iteration and knot by cmpc_solve_kernel (measured with ncu, see
 # profiles/ and DESIGN.md "flop accounting"), and the canonical dense figure of SURVEY.md 8(d)
 # (ncu smsp__sass_thread_inst_executed_op_{dfma x 2, dadd, dmul}_pred_on of one launch / (iterations x knots): captures prof_t96c
-# (monotone) and prof_pc (predictor-corrector: its second solve is two matrix-vector sweeps, few flops, and the monotone figure
+# (monotone) and prof_pc2 (predictor-corrector: its second solve is two matrix-vector sweeps, few flops, and the monotone figure
 # contains the refinement sweeps that the corrector replaces))
-FLOP_EXEC_PER_ITER_KNOT = {"monotone": 1.22e5, "mehrotra": 1.18e5}
+FLOP_EXEC_PER_ITER_KNOT = {"monotone": 1.22e5, "mehrotra": 1.19e5}
 FLOP_CANON_PER_ITER_KNOT = 422275.0
-# bytes per launch of icub3_b1024 (team 96, 7 teams / CTA in 3 groups): ncu captures prof_g3 (monotone), prof_pc (predictor-corrector)
-DRAM_TRAFFIC_PER_LAUNCH = {"monotone": 1.240e10, "mehrotra": 1.216e10}
+# bytes per launch of icub3_b1024 (team 96, 7 teams / CTA in 3 groups): ncu captures prof_g3 (monotone), prof_pc2 (predictor-corrector)
+DRAM_TRAFFIC_PER_LAUNCH = {"monotone": 1.240e10, "mehrotra": 1.197e10}
 FP64_PEAK_FALLBACK_TFLOPS = 37.0  # vendor figure (HGX B200 296 TF / 8); used only if the live DFMA probe fails
 
 
@@ -358,7 +358,7 @@ def main():
                         "iterations": int(iters_h[0]), "note": "batch of one instance, device resident, cold start; batches of at most one instance per SM run on the single-team kernel (128 threads, no register cap) unless a geometry is forced"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "traffic": DRAM_TRAFFIC_PER_LAUNCH[args.mu_strategy] if (args.workload == "icub3_b1024" and B == 1024) else None,
-                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu captures prof_pc / prof_g3 "
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu captures prof_pc2 / prof_g3 "
                                          "(profiles/r1_notes.md): the solver's scratch (iterate vectors + Riccati factors of 1036 "
                                          "resident teams) does not fit the 126 MB L2", "peak_source": peak_src, "kernel": "cmpc_solve_team_kernel",
                          "kernel_ms_per_launch": 1e3 * kernel_s, "flop_executed_per_launch": flop_exec,
