@@ -224,16 +224,20 @@ def main():
     d_lam = torch.zeros(B, m, dtype=torch.float64, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2
 
+    # the only exchange of the sharded job: gather per-instance results, overlapped with the next batch's
+    # solve on a side stream (sharding.AsyncGather): the ranks meet once, at the end of the timed region
+    gather = sharding.AsyncGather(world)
+
     def step():
         d_x.copy_(d_x0)
         obj, status, iters, _ = solver.solve(d_p, d_lbg, d_ubg, d_x, d_lam)
-        # the only exchange of the sharded job: gather per-instance results
-        sharding.gather_results(sharding.pack_results(obj, status, iters), world)
+        gather.submit(sharding.pack_results(obj, status, iters))
         return obj, status, iters
 
     for _ in range(args.warmup):
         flush.zero_()
         obj, status, iters = step()
+    gather.wait()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -253,16 +257,21 @@ def main():
         kev[s][0].record()
         obj, status, iters, _ = solver.solve(d_p, d_lbg, d_ubg, d_x, d_lam)
         kev[s][1].record()
-        sharding.gather_results(sharding.pack_results(obj, status, iters), world)
+        gather.submit(sharding.pack_results(obj, status, iters))
         ev[s][1].record()
+    tail = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    tail[0].record()
+    gathered = gather.wait()               # the timed region ends when every gather has landed
+    tail[1].record()
     torch.cuda.synchronize()
+    assert len(gathered) == args.steps and gathered[-1].shape[0] == world * B
     if world > 1:
         dist.barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = solver.launch_count() - launches0
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    t_dev = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    t_dev = (sum(a.elapsed_time(b) for a, b in ev) + tail[0].elapsed_time(tail[1])) * 1e-3
     t_kernel = sum(a.elapsed_time(b) for a, b in kev) * 1e-3
     tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
     if world > 1:

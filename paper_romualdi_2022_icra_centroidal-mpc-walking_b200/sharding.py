@@ -33,3 +33,32 @@ def gather_results(local: torch.Tensor, world: int, sizes: list[int] | None = No
     if sizes:
         out = [o[:s] for o, s in zip(out, sizes)]
     return torch.cat(out, dim=0)
+
+
+class AsyncGather:
+    """The gather of a batch's results overlapped with the solve of the next batch: the all_gather is enqueued on a side
+    stream behind an event of the producing stream, so a rank that finishes a batch early starts the next one instead of
+    waiting for the slowest rank at every batch (the ranks only meet in wait()).  CUDA / NCCL only; with world == 1 or on
+    CPU tensors it degenerates to gather_results."""
+
+    def __init__(self, world: int, sizes: list[int] | None = None):
+        self.world, self.sizes, self.pending = world, sizes, []
+        self.stream = torch.cuda.Stream() if (world > 1 and torch.cuda.is_available()) else None
+
+    def submit(self, local: torch.Tensor):
+        if self.stream is None or not local.is_cuda:
+            self.pending.append(gather_results(local, self.world, self.sizes))
+            return
+        ready = torch.cuda.Event()
+        ready.record()                                   # on the stream that produced `local`
+        local.record_stream(self.stream)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            self.pending.append(gather_results(local, self.world, self.sizes))
+
+    def wait(self) -> list[torch.Tensor]:
+        """makes the current stream wait for every submitted gather; returns the gathered results in submission order"""
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        out, self.pending = self.pending, []
+        return out

@@ -36,6 +36,11 @@ def _worker(rank, world, port, total, q):
     sizes = [b - a for a, b in (sh.shard_bounds(total, r, world) for r in range(world))]
     obj, status, iters = _fake_solve(torch.arange(lo, hi))
     allres = sh.gather_results(sh.pack_results(obj, status, iters), world, sizes)
+    ag = sh.AsyncGather(world, sizes)                   # bench.py's overlapped gather: on CPU tensors the same exchange
+    ag.submit(sh.pack_results(obj, status, iters))
+    ag.submit(sh.pack_results(obj + 1.0, status, iters))
+    got = ag.wait()
+    assert len(got) == 2 and torch.equal(got[0], allres) and torch.equal(got[1][:, 0], allres[:, 0] + 1.0) and not ag.pending
     t = torch.tensor([float(rank + 1)])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)          # the max-over-ranks timing reduction of bench.py
     q.put((rank, lo, hi, allres.numpy(), float(t.item())))
