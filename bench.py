@@ -364,7 +364,7 @@ def main():
                     "steps": k_e2e, "api": "cmpc_solve_host (pinned host buffers)"},
             "gpu_launches": int(launches),
             "latency": {"p50_single_solve_ms": float(np.median(lat)) if lat else None, "samples": len(lat),
-                        "iterations": int(iters_h[0]), "note": "batch of one instance, device resident, cold start; batches of at most one instance per SM run on the single-team kernel (128 threads, no register cap) unless a geometry is forced"},
+                        "iterations": int(iters_h[0]), "note": "batch of one instance, device resident, cold start; batches of up to 4 instances per SM run on independent single-team CTAs (128 threads; up to 2 per SM without a register cap) unless a geometry is forced"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "traffic": DRAM_TRAFFIC_PER_LAUNCH[args.mu_strategy] if (args.workload == "icub3_b1024" and B == 1024) else None,
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu captures prof_pc2 / prof_g3 "

@@ -725,10 +725,15 @@ CMPC_FN void step_pass(Team T, Cta& cta, const Config& cfg, ISmem& sm, double mu
 // teams that do not need it skip the work inside the phases (T.on) but never a barrier.
 // Batched arrays in the reference's CasADi order, instance major; x: in = initial guess, out = solution; lam: multipliers of g
 // (out; in when warm_duals).
+// Work distribution: the FIRST instance of a team is static, first_inst = team * (number of CTAs) + CTA, so that a batch
+// smaller than the number of resident teams is spread over all SMs (one team per SM first, then two, ...) instead of
+// filling the seven teams of the first CTAs; further instances come from the atomic queue, starting at queue_base = number
+// of teams of the grid.
 template <int NT, int G, class Cta>
 CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem& ism, const unsigned short* cmap, int batch,
                      const double* p_all, const double* lbg_all, const double* ubg_all, double* x_all, double* lam_all,
-                     double* obj_all, int* status_all, int* iters_all, int warm_duals, unsigned int* counter)
+                     double* obj_all, int* status_all, int* iters_all, int warm_duals, unsigned int* counter,
+                     int first_inst = 0, int queue_base = 1)
 {
     const int N = cfg.N, n = dim_x(N), np = dim_p(N), m = dim_g(N);
     WSmem& sm = ism.sw;
@@ -757,6 +762,7 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
     int nfilt = 0, it = 0, it_base = 0;
     bool pc = cfg.pc != 0;   // Mehrotra predictor-corrector barrier update (false: IPOPT's monotone update)
     bool redo = false;       // the predictor-corrector run of the instance failed: solve it again on the monotone path
+    bool first = true;       // the next instance of the team is its static one
 
     for (;;) {
         // ---- work queue: a team without an instance takes the next one
@@ -764,13 +770,17 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
         T.on = want;
         CMPC_LANES
             if (lane == 0) {
+                if (first) ism.inst = first_inst;
+                else {
 #if defined(__CUDA_ARCH__)
-                ism.inst = (int)atomicAdd(counter, 1u);
+                    ism.inst = queue_base + (int)atomicAdd(counter, 1u);
 #else
-                ism.inst = (int)((*counter)++);
+                    ism.inst = queue_base + (int)((*counter)++);
 #endif
+                }
             }
         CMPC_LANES_END
+        if (want) first = false;
         bool fresh = false;
         if (want) {
             inst = ism.inst;

@@ -172,7 +172,8 @@ cmpc_solve_team_kernel(const __grid_constant__ Config cfg, int batch, const doub
     cta.tid = T.lane; cta.nt = NT; cta.warp = T.lane >> 5; cta.lane = T.lane & 31; cta.wsize = 32;
     if constexpr (!(NT == 32 && G == 1)) { cta.red = sm.sw.red; cta.bar = G > 1 ? team + 1 : 0; }
     double* base = work + ((size_t)blockIdx.x * G + team) * work_stride;
-    ipm_run<NT, G>(T, cta, cfg, base, sm, cmap, batch, p, lbg, ubg, x, lam, obj, status, iters, warm_duals, counter);
+    ipm_run<NT, G>(T, cta, cfg, base, sm, cmap, batch, p, lbg, ubg, x, lam, obj, status, iters, warm_duals, counter,
+                   team * (int)gridDim.x + (int)blockIdx.x, G * (int)gridDim.x);
 }
 
 // warm-start shift: one CTA per instance, the vector is staged in shared memory so that loads and stores are coalesced
@@ -578,15 +579,33 @@ int cmpc_solve_batched(cmpc_handle h, int batch, const double* d_p, const double
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(h->device));
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
-    if (h->latency_path && batch <= h->sm_count && (size_t)batch <= h->work_slots) {
-        cmpc_solve_team_kernel<128, 1, 1><<<batch, 128, (int)sizeof(ISmem), st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj,
-                                                                                 d_status, d_iters, warm_duals, h->d_work,
-                                                                                 h->work_stride, h->d_counter, h->d_cmap, 1);
+    // small batches are latency bound: independent single-team CTAs of 128 threads (no lock-step, no 80-register cap) beat the
+    // seven-team CTAs while at most four of them share an SM (profiles/r1_notes.md): up to 2 per SM the kernel compiled
+    // without a register cap (254 registers, two CTAs run as fast as one), up to 4 per SM the one compiled for 4 CTAs (128)
+    const bool mid_persist = getenv("CMPC_MID_PERSIST") != nullptr;  // experiment: four single-team CTAs per SM for every batch size
+    if (h->latency_path && (size_t)4 * h->sm_count <= h->work_slots && (batch <= 4 * h->sm_count || mid_persist)) {
+        // shared-memory carve-out: just what the resident CTAs need, the rest of the 256 KB stays L1 (a lone team is 10 % faster
+        // with L1 behind its scratch vectors and spills than with the carve-out at its maximum)
+        const int lgrid = std::min(batch, 4 * h->sm_count);
+        const int per_sm = (lgrid + h->sm_count - 1) / h->sm_count;
+        int pct = (int)((100.0 * per_sm * (sizeof(ISmem) + 1024)) / (228.0 * 1024.0)) + 1;
+        if (pct > 100) pct = 100;
+        if (per_sm <= 2) {
+            cudaFuncSetAttribute((const void*)cmpc_solve_team_kernel<128, 1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cmpc_solve_team_kernel<128, 1, 1><<<lgrid, 128, (int)sizeof(ISmem), st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj,
+                                                                                     d_status, d_iters, warm_duals, h->d_work,
+                                                                                     h->work_stride, h->d_counter, h->d_cmap, 1);
+        } else {
+            cudaFuncSetAttribute((const void*)cmpc_solve_team_kernel<128, 1, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cmpc_solve_team_kernel<128, 1, 4><<<lgrid, 128, (int)sizeof(ISmem), st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj,
+                                                                                     d_status, d_iters, warm_duals, h->d_work,
+                                                                                     h->work_stride, h->d_counter, h->d_cmap, 1);
+        }
         h->launches++;
         CK(cudaGetLastError());
         return CMPC_OK;
     }
-    int grid = std::min((batch + h->lockstep - 1) / h->lockstep, h->grid);
+    int grid = std::min(batch, h->grid);  // a small batch is spread over the SMs (static first instance: team * grid + CTA)
 #define X(NT, G, C)                                                                                                      \
     if (h->threads == NT && h->lockstep == G)                                                                            \
         cmpc_solve_team_kernel<NT, G, C><<<grid, NT * G, h->smem, st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj, \

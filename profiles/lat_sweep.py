@@ -1,0 +1,21 @@
+"""Single-team (latency) kernel with k CTAs per SM: usage CMPC_LATENCY_MULT=k [CMPC_B200_LIB=...] python profiles/lat_sweep.py B1 B2 ..."""
+import importlib, os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+PKG = "paper_romualdi_2022_icra_centroidal-mpc-walking_b200"
+pkg = importlib.import_module(PKG); wl = importlib.import_module(PKG + ".workloads")
+import torch
+def run(B, reps=3):
+    s = pkg.BatchedCentroidalMPC(pkg.icub3_config())
+    w = wl.walk_batch(N=15, dT=0.1, B=B, seed=0, state_noise=1.0, step_adjust=False)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    p, lb, ub, x0 = t(w["p"]), t(w["lbg"]), t(w["ubg"]), t(w["x0"])
+    ms = []
+    for r in range(reps + 1):
+        x = x0.clone(); a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); obj, st, it, _ = s.solve(p, lb, ub, x); b.record(); torch.cuda.synchronize()
+        if r: ms.append(a.elapsed_time(b))
+    s.close(); return float(np.median(ms)), int((st == 0).sum().item())
+for B in [int(a) for a in sys.argv[1:]] or [148, 296]:
+    ms, conv = run(B)
+    print("lat_mult", os.environ.get("CMPC_LATENCY_MULT", "1"), "lib", os.path.basename(os.environ.get("CMPC_B200_LIB", "default")), "batch", B, f"{ms:.2f} ms", f"{B / ms:.1f} solves/ms", "converged", conv, flush=True)

@@ -443,3 +443,25 @@ def test_ini_tolerances(oracle, workloads, tol, strategy):
         assert abs(int(iters[b]) - st[b].iters) <= 1, (b, iters[b], st[b].iters)
         assert abs(obj[b] - st[b].obj) <= 1e-6 * max(1.0, abs(st[b].obj)), (b, obj[b], st[b].obj)
         assert abs(obj[b] - stt[b].obj) <= 1e-3 * max(1.0, abs(stt[b].obj)), (b, obj[b], stt[b].obj)
+
+
+def test_small_batch_kernels_agree_with_the_lockstep_kernel(workloads):
+    """default geometry: batches of up to 2 / up to 4 instances per SM run on independent single-team CTAs (the kernel
+    without a register cap / the one compiled for four CTAs per SM), larger ones on the seven-team lock-step CTAs.  Same
+    solutions from all three (different team sizes: rounding-level differences only)."""
+    P = pkg()
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    w = workloads.walk_batch(N=12, B=4 * sms, seed=17, state_noise=1.5, yaw_range=0.2)
+    ref = P.BatchedCentroidalMPC(P.ergocub_config(teams_per_cta=7))
+    auto = P.BatchedCentroidalMPC(P.ergocub_config())
+    xr, lr, objr, str_, itr = ref.solve_host(w["p"], w["lbg"], w["ubg"], w["x0"])
+    assert (str_ == 0).all()
+    for B in (sms + 3, 2 * sms, 2 * sms + 1, 3 * sms + 5, 4 * sms):
+        n0 = auto.launch_count()
+        x, lam, obj, status, iters = auto.solve_host(w["p"][:B], w["lbg"][:B], w["ubg"][:B], w["x0"][:B])
+        assert auto.launch_count() == n0 + 1
+        assert (status == 0).all(), (B, np.bincount(status))
+        assert np.max(np.abs(x - xr[:B])) < 1e-6 and np.max(np.abs(obj - objr[:B]) / np.abs(objr[:B])) < 1e-9, B
+        assert np.max(np.abs(iters - itr[:B])) <= 1
+    ref.close()
+    auto.close()
