@@ -6,7 +6,9 @@
 A "step" = one pass of the hot path (cmpc_solve_batched: the full interior-point solve of every instance, cold start
 from the same x0) over one batch of synthetic MPC instances.  Default workload = BASELINE.json configs[1]:
 batch 1024 iCub3 instances (iCubGazeboV3/centroidal_mpc.ini: N = 15, dT = 0.1), randomised CoM / momentum initial
-states, step adjustment off, ipopt tolerance 1e-8 -- per GPU (weak scaling over --gpus).
+states, step adjustment off, ipopt tolerance 1e-8 -- per GPU (weak scaling over --gpus).  --tol defaults to the
+ipopt_tolerance of the workload's robot ini (iCub3: 1e-8; ergoCubGazeboV1_1: 1e-4); --mu-strategy selects the barrier update
+(mehrotra = library default, monotone = IPOPT's default path).
   value    : solves/s with inputs resident in HBM, CUDA-event time of the K steps (max over ranks)
   e2e      : solves/s through cmpc_solve_host with pinned HOST buffers (H2D + solve + D2H inside the timed region)
   roofline : executed FP64 flop / kernel time against the measured FP64 FMA peak (the kernel is FP64 CUDA-core
@@ -40,6 +42,8 @@ FLOP_EXEC_PER_ITER_KNOT = {"monotone": 1.22e5, "mehrotra": 1.19e5}
 FLOP_CANON_PER_ITER_KNOT = 422275.0
 # bytes per launch of icub3_b1024 (team 96, 7 teams / CTA in 3 groups): ncu captures prof_g3 (monotone), prof_pc2 (predictor-corrector)
 DRAM_TRAFFIC_PER_LAUNCH = {"monotone": 1.240e10, "mehrotra": 1.197e10}
+# ipopt_tolerance of the robot ini each workload is built from (config/robots/<robot>/centroidal_mpc.ini)
+INI_TOLERANCE = {"icub3_b1024": 1e-8, "ergocub_b65536": 1e-4}
 FP64_PEAK_FALLBACK_TFLOPS = 37.0  # vendor figure (HGX B200 296 TF / 8); used only if the live DFMA probe fails
 
 
@@ -151,7 +155,7 @@ def run_reference(args):
     sample = min(w["p"].shape[0], max(64, 16 * cores))
     times = []
     for s in range(args.warmup + args.steps):
-        rate, dt, ok, its = cpu_oracle_rate(ocfg, w, sample, cores, 1e-8)
+        rate, dt, ok, its = cpu_oracle_rate(ocfg, w, sample, cores, args.tol)
         if s >= args.warmup:
             times.append(dt)
     t = float(np.sum(times))
@@ -161,8 +165,8 @@ def run_reference(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "note": "each step = bounded sample of the workload"},
             "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample} instances of {args.workload} per step, tol 1e-8, "
-                                       f"{ok}/{sample} converged, mean {its:.1f} iterations"},
+                             "sample": f"{sample} instances of {args.workload} per step, tol {args.tol:g}, "
+                                       f"{ok}/{sample} converged, mean {its:.1f} iterations, tol {args.tol:g}"},
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -174,7 +178,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="icub3_b1024")
-    ap.add_argument("--tol", type=float, default=1e-8)
+    ap.add_argument("--tol", type=float, default=None,
+                    help="ipopt_tolerance; default = the value of the workload's robot ini (iCubGazeboV3: 1e-8, the BLF default, "
+                         "its ini leaves the key commented out; ergoCubGazeboV1_1: 1e-4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--team", type=int, default=0, help="threads per instance (32/64/96/128), 0 = library default")
     ap.add_argument("--lockstep", type=int, default=0, help="teams per CTA walking in lock-step (1, 3, 7; 0 = library default)")
@@ -185,6 +191,8 @@ def main():
     ap.add_argument("--mu-strategy", default="mehrotra", choices=["mehrotra", "monotone"],
                     help="barrier update of the solve: Mehrotra predictor-corrector (library default) or IPOPT's monotone update")
     args = ap.parse_args()
+    if args.tol is None:
+        args.tol = INI_TOLERANCE[args.workload]
     if args.impl == "reference":
         return run_reference(args)
 
@@ -285,7 +293,7 @@ def main():
     lat = []
     if rank == 0:
         x1 = d_x0[:1].clone()
-        for j in range(15):
+        for j in range(35):
             x1.copy_(d_x0[:1])
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
@@ -363,7 +371,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": k_e2e, "api": "cmpc_solve_host (pinned host buffers)"},
             "gpu_launches": int(launches),
-            "latency": {"p50_single_solve_ms": float(np.median(lat)) if lat else None, "samples": len(lat),
+            "latency": {"p50_single_solve_ms": float(np.median(lat)) if lat else None,
+                        "p95_single_solve_ms": float(np.percentile(lat, 95)) if lat else None, "samples": len(lat),
                         "iterations": int(iters_h[0]), "note": "batch of one instance, device resident, cold start; batches of up to 4 instances per SM run on independent single-team CTAs (128 threads; up to 2 per SM without a register cap) unless a geometry is forced"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "traffic": DRAM_TRAFFIC_PER_LAUNCH[args.mu_strategy] if (args.workload == "icub3_b1024" and B == 1024) else None,
