@@ -103,8 +103,11 @@ int cmpc_destroy(cmpc_handle h);
  * Solves `batch` independent instances  min f(x, p)  s.t.  lbg <= g(x, p) <= ubg.
  * DEVICE pointers.  d_x: in = initial guess (warm start), out = solution.  d_lam_g: out = multipliers of g
  * (CasADi/IPOPT sign: >= 0 at an active upper bound); read as initial multipliers when warm_duals != 0.
- * d_obj[batch], d_status[batch], d_iters[batch] may be null.  `stream` is a cudaStream_t (null = default stream);
- * the call is asynchronous with respect to the host. */
+ * d_obj[batch], d_status[batch], d_iters[batch] may be null.  d_iters counts every interior-point iteration spent on
+ * the instance (an instance handed from the predictor-corrector to the monotone path reports the sum).  `stream` is a
+ * cudaStream_t (null = default stream); the call is asynchronous with respect to the host.  One kernel launch per call:
+ * batches of up to 4 instances per SM run on independent single-team CTAs, larger ones on persistent CTAs of seven
+ * teams walking in lock-step. */
 int cmpc_solve_batched(cmpc_handle h, int batch, const double* d_p, const double* d_lbg, const double* d_ubg,
                        double* d_x, double* d_lam_g, double* d_obj, int* d_status, int* d_iters, int warm_duals,
                        void* stream);
