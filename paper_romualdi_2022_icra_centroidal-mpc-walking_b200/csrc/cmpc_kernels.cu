@@ -582,8 +582,9 @@ int cmpc_solve_batched(cmpc_handle h, int batch, const double* d_p, const double
     // small batches are latency bound: independent single-team CTAs of 128 threads (no lock-step, no 80-register cap) beat the
     // seven-team CTAs while at most four of them share an SM (profiles/r1_notes.md): up to 2 per SM the kernel compiled
     // without a register cap (254 registers, two CTAs run as fast as one), up to 4 per SM the one compiled for 4 CTAs (128)
-    const bool mid_persist = getenv("CMPC_MID_PERSIST") != nullptr;  // experiment: four single-team CTAs per SM for every batch size
-    if (h->latency_path && (size_t)4 * h->sm_count <= h->work_slots && (batch <= 4 * h->sm_count || mid_persist)) {
+    // (CMPC_SINGLE_TEAM_PERSIST=1, experiments only: four single-team CTAs per SM for every batch size: 59 solves/ms against 69)
+    const bool st_persist = getenv("CMPC_SINGLE_TEAM_PERSIST") != nullptr;
+    if (h->latency_path && (size_t)4 * h->sm_count <= h->work_slots && (batch <= 4 * h->sm_count || st_persist)) {
         // shared-memory carve-out: just what the resident CTAs need, the rest of the 256 KB stays L1 (a lone team is 10 % faster
         // with L1 behind its scratch vectors and spills than with the carve-out at its maximum)
         const int lgrid = std::min(batch, 4 * h->sm_count);

@@ -1,4 +1,6 @@
-"""Single-team (latency) kernel with k CTAs per SM: usage CMPC_LATENCY_MULT=k [CMPC_B200_LIB=...] python profiles/lat_sweep.py B1 B2 ..."""
+"""Launch time of small and mid-size batches (iCub3, N = 15, cold start) with the default dispatch: up to 2 / up to 4 instances per
+SM on independent single-team CTAs, larger batches on the seven-team lock-step CTAs (CMPC_NO_LATENCY_PATH=1 forces the latter,
+CMPC_SINGLE_TEAM_PERSIST=1 the former for every size).  usage: [CMPC_B200_LIB=...] python profiles/lat_sweep.py B1 B2 ..."""
 import importlib, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -18,4 +20,4 @@ def run(B, reps=3):
     s.close(); return float(np.median(ms)), int((st == 0).sum().item())
 for B in [int(a) for a in sys.argv[1:]] or [148, 296]:
     ms, conv = run(B)
-    print("lat_mult", os.environ.get("CMPC_LATENCY_MULT", "1"), "lib", os.path.basename(os.environ.get("CMPC_B200_LIB", "default")), "batch", B, f"{ms:.2f} ms", f"{B / ms:.1f} solves/ms", "converged", conv, flush=True)
+    print("lib", os.path.basename(os.environ.get("CMPC_B200_LIB", "default")), "batch", B, f"{ms:.2f} ms", f"{B / ms:.1f} solves/ms", "converged", conv, flush=True)
