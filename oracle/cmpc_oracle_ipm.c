@@ -76,6 +76,7 @@ void cmpc_oracle_ipm_default_opts(cmpc_oracle_ipm_opts* o)
 #define KAPPA_C 0.25
 #define NEG_CURV_TOL 1e-10
 #define MAX_FILTER 64
+#define PC_MAX_ITER 50 /* predictor-corrector iterations after which an instance is handed to the monotone path */
 
 /* ------------------------------------------------------------------ banded LU (LAPACK dgbtf2 / dgbtrs layout) */
 typedef struct band {
@@ -511,7 +512,7 @@ static int ipm_core(const cmpc_oracle_nlp_fn* F, int N, const cmpc_oracle_ipm_op
             fprintf(stderr, "it %3d f %.10e  E0 %.2e (d %.2e v %.2e c %.2e) mu %.1e dw %.1e\n", it, f, e0.E, e0.dual,
                     e0.viol, e0.compl_, mu, dw_last);
         if (e0.E <= opts->tol && e0.dual <= 1.0 && e0.viol <= 1e-4 && e0.compl_ <= 1e-4) { status = 0; break; }
-        if (it == opts->max_iter) { status = 1; break; }
+        if (it == opts->max_iter || (mehrotra && it == PC_MAX_ITER)) { status = 1; break; }
         /* barrier parameter update (eq. 7); in predictor-corrector mode mu follows from the affine step below */
         while (!mehrotra) {
             errs em = kkt_error(W, mu, scratch);
@@ -675,7 +676,7 @@ int cmpc_oracle_ipm_solve_fn(const cmpc_oracle_nlp_fn* F, int N, const cmpc_orac
     memcpy(x0, x, sizeof(double) * F->n);
     if (lam_g) memcpy(l0, lam_g, sizeof(double) * F->m);
     int st = ipm_core(F, N, opts, 1, p, lbg, ubg, x, lam_g, stats);
-    if (st >= 1 && st <= 3) {
+    if (st == 2 || st == 3 || (st == 1 && stats->iters < opts->max_iter)) {   /* an exhausted max_iter is final */
         cmpc_oracle_ipm_stats s1 = *stats;
         memcpy(x, x0, sizeof(double) * F->n);
         if (lam_g) memcpy(lam_g, l0, sizeof(double) * F->m);

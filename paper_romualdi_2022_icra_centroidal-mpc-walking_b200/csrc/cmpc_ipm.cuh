@@ -1083,7 +1083,8 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
 #endif
         if (act) ++it;
         // an instance the predictor-corrector path cannot finish starts again from its initial point on the monotone path
-        if (pc && fin >= 1 && fin <= 3) { pc = false; redo = true; it_base += it; fin = -1; }
+        // (an exhausted ipopt_max_iteration is final, as in IPOPT: only the predictor-corrector's own iteration cap hands over)
+        if (pc && (fin == 2 || fin == 3 || (fin == 1 && it < cfg.max_iter))) { pc = false; redo = true; it_base += it; fin = -1; }
 
         // ---- write-back of the instances that finished in this round (solution to the CasADi order), then back to the queue
         const bool done = fin >= 0;

@@ -465,3 +465,17 @@ def test_small_batch_kernels_agree_with_the_lockstep_kernel(workloads):
         assert np.max(np.abs(iters - itr[:B])) <= 1
     ref.close()
     auto.close()
+
+
+@pytest.mark.parametrize("strategy", STRATEGIES)
+def test_iteration_limit_is_final(workloads, strategy):
+    """ipopt_max_iteration (the reference's ini files carry a commented `ipopt_max_iteration 14`): an instance that runs into
+    the limit reports CMPC_STATUS_MAX_ITER with exactly that many iterations -- the predictor-corrector does not start a
+    monotone re-solve on top of an exhausted budget -- and its x is the last iterate."""
+    P = pkg()
+    w = workloads.walk_batch(N=12, B=8, seed=2, state_noise=1.0)
+    s = P.BatchedCentroidalMPC(P.ergocub_config(ipopt_max_iteration=5, **strategy_kw(strategy)))
+    x, lam, obj, status, iters = s.solve_host(w["p"], w["lbg"], w["ubg"], w["x0"])
+    s.close()
+    assert (status == 1).all() and (iters == 5).all(), (status, iters)
+    assert np.isfinite(x).all() and np.any(x != w["x0"])
