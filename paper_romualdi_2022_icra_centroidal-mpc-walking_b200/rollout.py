@@ -21,11 +21,58 @@ from .workloads import walk_batch
 PUSH_THRESHOLD = 0.7  # WholeBodyQPBlock.cpp:1018
 
 
+class WalkSchedule:
+    """The walk schedule of workloads.walk_batch as a device-resident table: the formal inputs (p, lbg, ubg, x0) and the
+    contact bookkeeping of an instance depend on its phase only (yaw 0, no state noise), are periodic in the phase with
+    period P = 2 (double support + single support) knots from the second cycle on, up to a translation of every
+    x coordinate by one stride per cycle.  Built once from walk_batch on the host (phases 0 .. 2 P - 1: start-up cycle and
+    first steady cycle; the x-coordinate mask = entries that move by exactly one stride between phase ph and ph + P),
+    evaluated per tick with two gathers on the device: no host-side generation and no H2D copy of the inputs per tick
+    (the role of the planner + updateContactPhaseList feeding setContactPhaseList, CentroidalMPCBlock.cpp:596-609)."""
+
+    def __init__(self, N: int, dT: float, device, step_adjust: bool = True, **kw):
+        probe = walk_batch(N=N, dT=dT, B=1, phase=0, step_adjust=step_adjust, **kw)
+        self.N, self.dT, self.device = N, dT, device
+        ds = int(round(kw.get("ds_time", 0.3) / dT)); ss = int(round(kw.get("ss_time", 0.5) / dT))
+        self.P = P = 2 * (ds + ss)
+        self.stride = 2.0 * kw.get("step_length", 0.1)
+        a = walk_batch(N=N, dT=dT, B=2 * P, phase=np.arange(2 * P), step_adjust=step_adjust, **kw)
+        b = walk_batch(N=N, dT=dT, B=P, phase=np.arange(2 * P, 3 * P), step_adjust=step_adjust, **kw)
+        to = lambda x, dt=torch.float64: torch.from_numpy(np.ascontiguousarray(x)).to(device=device, dtype=dt)  # noqa: E731
+        self.tab, self.mask = {}, {}
+        for key in ("p", "lbg", "ubg", "x0", "comref"):
+            t = a[key].reshape(2 * P, -1)
+            d = b[key].reshape(P, -1) - t[P:]
+            m = np.abs(d - self.stride) < 1e-12                     # x coordinates: one stride further every cycle
+            assert np.all(m | (np.nan_to_num(d, nan=0.0, posinf=0.0, neginf=0.0) == 0.0)), key
+            assert np.all(m == m[0]), key                          # the same entries for every phase
+            self.tab[key], self.mask[key] = to(t), to(m[0].astype(np.float64))
+        self.same = to(np.moveaxis(a["same_contact"], 1, 0), torch.bool)      # (2P, NC, N+1)
+        self.stance0 = to(np.moveaxis(a["stance0"], 1, 0), torch.bool)        # (2P, NC)
+        del probe
+
+    def __call__(self, phase: torch.Tensor):
+        """phase: (B,) int64 device tensor -> dict like walk_batch (device tensors; comref (B, N+1, 3))"""
+        P = self.P
+        steady = phase >= 2 * P
+        idx = torch.where(steady, P + phase % P, phase)
+        shift = torch.where(steady, (torch.div(phase, P, rounding_mode="floor") - 1).double() * self.stride,
+                            torch.zeros_like(phase, dtype=torch.float64))
+        out = {k: self.tab[k][idx] + shift[:, None] * self.mask[k][None, :] for k in self.tab}
+        out["comref"] = out["comref"].view(-1, self.N + 1, 3)
+        out["same_contact"] = self.same[idx].permute(1, 0, 2)      # (NC, B, N+1) as in walk_batch
+        out["stance0"] = self.stance0[idx].permute(1, 0)           # (NC, B)
+        return out
+
+
 def closed_loop_rollout(solver: BatchedCentroidalMPC, B: int, ticks: int, seed: int = 0, dT: float = 0.1, wbc_dt: float = 0.002,
                         push_prob: float = 1.0, push_range=(1.0, 3.0), step_adjust: bool = True, yaw_range: float = 0.0,
-                        time_device: bool = False):
+                        time_device: bool = False, host_schedule: bool = False):
     """returns dict of per-instance numpy arrays: converged ticks, iterations, max CoM tracking error, min CoM height;
-    time_device = True adds "device_ms": CUDA-event time of the kernels of every tick (shift + solve + plant)"""
+    time_device = True adds "device_ms": CUDA-event time of the kernels of every tick (shift + solve + plant).
+    The contact schedule of every tick comes from the device-resident WalkSchedule table (no host work, no H2D copy and no
+    host synchronisation inside the loop); host_schedule = True (or yaw_range > 0: random footstep yaw is not tabulated)
+    regenerates it with workloads.walk_batch on the host every tick, as the first version of this driver did."""
     N, dev = solver.N, solver.device
     L = Layout(N)
     rng = np.random.default_rng(seed)
@@ -36,27 +83,35 @@ def closed_loop_rollout(solver: BatchedCentroidalMPC, B: int, ticks: int, seed: 
     mag = rng.uniform(*push_range, size=B)
     push_vec = np.stack([mag * np.cos(ang), mag * np.sin(ang), np.zeros(B)], axis=1)
     substeps = int(round(dT / wbc_dt))
+    host_schedule = host_schedule or yaw_range > 0
 
     tens = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    sched = None if host_schedule else WalkSchedule(N, dT, dev, step_adjust=step_adjust)
+    d_phase0, d_push_tick, d_push_len, d_push_vec = tens(phase0), tens(push_tick), tens(push_len), tens(push_vec)
+    push_big = d_push_vec.norm(dim=1, keepdim=True) >= PUSH_THRESHOLD
     state = None                                                # (B, 9) com, dcom, h of the plant
     foot = None                                                 # (B, 2, 3) actual foot positions
     d_x = d_lam = None
-    conv = np.zeros(B, dtype=np.int64)
-    iters_sum = np.zeros(B, dtype=np.int64)
-    err_max = np.zeros(B)
-    zmin = np.full(B, np.inf)
+    conv = torch.zeros(B, dtype=torch.int64, device=dev)
+    iters_sum = torch.zeros(B, dtype=torch.int64, device=dev)
+    err_max = torch.zeros(B, dtype=torch.float64, device=dev)
+    zmin = torch.full((B,), float("inf"), dtype=torch.float64, device=dev)
     g0 = L.p_glob()
     events = []
     for t in range(ticks):
-        w = walk_batch(N=N, dT=dT, B=B, seed=seed, phase=phase0 + t, step_adjust=step_adjust, yaw_range=yaw_range)
-        p, lbg, ubg = tens(w["p"]), tens(w["lbg"]), tens(w["ubg"])
-        active = (push_tick >= 0) & (t >= push_tick) & (t < push_tick + push_len)
-        ext = np.where(active[:, None], push_vec, 0.0)
-        ext_mpc = np.where(np.linalg.norm(ext, axis=1, keepdims=True) >= PUSH_THRESHOLD, ext, 0.0)
+        if host_schedule:
+            w = walk_batch(N=N, dT=dT, B=B, seed=seed, phase=phase0 + t, step_adjust=step_adjust, yaw_range=yaw_range)
+            w = {k: (tens(v) if isinstance(v, np.ndarray) else v) for k, v in w.items()}
+        else:
+            w = sched(d_phase0 + t)
+        p, lbg, ubg = w["p"], w["lbg"], w["ubg"]
+        active = (d_push_tick >= 0) & (t >= d_push_tick) & (t < d_push_tick + d_push_len)
+        ext = torch.where(active[:, None], d_push_vec, torch.zeros_like(d_push_vec))
+        ext_mpc = torch.where(push_big, ext, torch.zeros_like(ext))
         if state is None:
             state = p[:, g0:g0 + 9].clone()
             foot = torch.stack([p[:, L.p_cur(c):L.p_cur(c) + 3] for c in range(2)], dim=1).clone()
-            d_x = tens(w["x0"])
+            d_x = w["x0"].clone()
             d_lam = torch.zeros(B, L.m, dtype=torch.float64, device=dev)
             warm = False
         else:
@@ -72,8 +127,8 @@ def closed_loop_rollout(solver: BatchedCentroidalMPC, B: int, ticks: int, seed: 
         p[:, g0:g0 + 9] = state
         lbg[:, 0:9] = state
         ubg[:, 0:9] = state
-        p[:, L.p_extf(0):L.p_extf(0) + 3] = tens(ext_mpc)
-        same, stance0 = tens(w["same_contact"]), tens(w["stance0"])
+        p[:, L.p_extf(0):L.p_extf(0) + 3] = ext_mpc
+        same, stance0 = w["same_contact"], w["stance0"]
         for c in range(2):
             nom = p[:, L.p_nom(c, 0):L.p_nom(c, 0) + 3 * (N + 1)].view(B, N + 1, 3)
             delta = (foot[:, c] - nom[:, 0]) * stance0[c].unsqueeze(1)          # stance: the contact is where the foot landed
@@ -87,21 +142,20 @@ def closed_loop_rollout(solver: BatchedCentroidalMPC, B: int, ticks: int, seed: 
         obj, status, iters, _ = solver.solve(p, lbg, ubg, d_x, d_lam, warm_duals=warm)
         # plant: RK4 under the knot-0 forces (+ the push), then the next tick's foot positions from the MPC's own plan
         ext6 = torch.zeros(B, 6, dtype=torch.float64, device=dev)
-        ext6[:, :3] = tens(ext)
+        ext6[:, :3] = ext
         solver.rollout_plant(d_x, p, state, wbc_dt, substeps, ext=ext6)
         if time_device:
             ev[1].record()
             events.append(ev)
         for c in range(2):
             foot[:, c] = d_x[:, L.x_pos(c, 1):L.x_pos(c, 1) + 3]
-        st = status.cpu().numpy()
-        conv += st == 0
-        iters_sum += iters.cpu().numpy()
-        com = state[:, 0:3].cpu().numpy()
+        conv += (status == 0)
+        iters_sum += iters
         ref = w["comref"][:, 1]                                   # the reference of the knot the plant has just reached
-        err_max = np.maximum(err_max, np.linalg.norm(com[:, :2] - ref[:, :2], axis=1))
-        zmin = np.minimum(zmin, com[:, 2])
-    out = dict(converged_ticks=conv, iterations=iters_sum, com_err_max=err_max, com_z_min=zmin, push_tick=push_tick, ticks=ticks)
+        err_max = torch.maximum(err_max, (state[:, 0:2] - ref[:, 0:2]).norm(dim=1))
+        zmin = torch.minimum(zmin, state[:, 2])
+    out = dict(converged_ticks=conv.cpu().numpy(), iterations=iters_sum.cpu().numpy(), com_err_max=err_max.cpu().numpy(),
+               com_z_min=zmin.cpu().numpy(), push_tick=push_tick, ticks=ticks)
     if time_device:
         torch.cuda.synchronize()
         out["device_ms"] = float(sum(a.elapsed_time(b) for a, b in events))
