@@ -76,6 +76,11 @@ typedef struct cmpc_config {
                                             /* CMPC_MU_MEHROTRA = predictor-corrector (mu from the affine-scaling step,   */
                                             /* second-order corrector on the same factorisation, ~0.63 x the iterations;  */
                                             /* same termination test; an instance it cannot finish is re-solved monotone) */
+    double warm_start_mu_init;              /* solves that start from given multipliers (warm_duals != 0): floor mu / slack of   */
+                                            /* the bound multipliers and first barrier parameter of the monotone update;      */
+                                            /* 0 = default 0.01 (closed loop at tol 1e-4: 4.4 instead of 5.4 iterations per   */
+                                            /* tick with IPOPT's cold-start value 0.1; smaller values lengthen the slowest    */
+                                            /* solves of a batch)                                                            */
 } cmpc_config;
 #define CMPC_MU_DEFAULT 0
 #define CMPC_MU_MONOTONE 1

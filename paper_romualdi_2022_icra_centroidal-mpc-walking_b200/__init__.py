@@ -29,7 +29,7 @@ class CmpcConfig(C.Structure):
                 ("mu_init", C.c_double), ("bound_relax_factor", C.c_double), ("bound_push", C.c_double),
                 ("infinity", C.c_double), ("device", C.c_int), ("threads_per_instance", C.c_int),
                 ("ctas_per_sm", C.c_int), ("teams_per_cta", C.c_int), ("lockstep_groups", C.c_int),
-                ("mu_strategy", C.c_int)]
+                ("mu_strategy", C.c_int), ("warm_start_mu_init", C.c_double)]
 
 
 _dp = C.POINTER(C.c_double)

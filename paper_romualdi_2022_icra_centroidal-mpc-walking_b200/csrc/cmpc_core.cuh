@@ -47,6 +47,8 @@ struct Config {
     double bound_push;   // bound_push = bound_frac
     double inf_bound;    // nlp_upper_bound_inf
     int pc;              // 1: Mehrotra predictor-corrector barrier update, 0: IPOPT's monotone update (mu_strategy)
+    double mu_warm;      // barrier parameter of a solve that starts from given multipliers (warm_duals): floor of the bound
+                         // multipliers mu_warm / slack and first mu of the monotone update
 };
 
 struct Instance {  // CasADi order, read only

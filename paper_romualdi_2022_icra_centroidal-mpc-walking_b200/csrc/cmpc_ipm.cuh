@@ -879,7 +879,7 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
             if (fresh && bad[0] != 0.0) { fin = 4; fresh = false; f = 0; it = 0; E0 = 0; }
             // initial point: slacks pushed inside their bounds (bound_push / bound_frac), bound multipliers 1
             T.on = fresh;
-            if (fresh) { mu = cfg.mu_init; tau = fmax(TAU_MIN, 1.0 - mu); nfilt = 0; dw_last = 0.0; it = 0; }
+            if (fresh) { mu = warm ? cfg.mu_warm : cfg.mu_init; tau = fmax(TAU_MIN, 1.0 - mu); nfilt = 0; dw_last = 0.0; it = 0; }
             eval_point<NT, G>(T, cta, cfg, ism, w.z, w.sl);  // path row values (the slacks are not set yet)
     CMPC_LANES
         for (int it = lane; it < N * 64; it += NT) {
@@ -901,8 +901,8 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
             double zl = hl ? 1.0 : 0.0, zu = hu ? 1.0 : 0.0;
             if (warm) {
                 const double yv = w.yp[pr];
-                if (hl) zl = fmax(yv < 0 ? -yv : 0.0, cfg.mu_init / (s - sl));
-                if (hu) zu = fmax(yv > 0 ? yv : 0.0, cfg.mu_init / (su - s));
+                if (hl) zl = fmax(yv < 0 ? -yv : 0.0, cfg.mu_warm / (s - sl));
+                if (hu) zu = fmax(yv > 0 ? yv : 0.0, cfg.mu_warm / (su - s));
             }
             w.zl[pr] = zl; w.zu[pr] = zu;
         }

@@ -438,6 +438,7 @@ int cmpc_default_config(cmpc_config* c)
     c->ipopt_tolerance = 1e-8; c->ipopt_max_iteration = 200; c->mu_init = 0.1; c->bound_relax_factor = 1e-8;
     c->bound_push = 0.01; c->infinity = 1e19; c->device = 0; c->threads_per_instance = 0; c->ctas_per_sm = 0;
     c->mu_strategy = CMPC_MU_DEFAULT;
+    c->warm_start_mu_init = 0.01;
     return CMPC_OK;
 }
 
@@ -499,6 +500,7 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
     c.tol = u->ipopt_tolerance > 0 ? u->ipopt_tolerance : 1e-8;
     c.max_iter = u->ipopt_max_iteration > 0 ? u->ipopt_max_iteration : 200;
     c.mu_init = u->mu_init > 0 ? u->mu_init : 0.1;
+    c.mu_warm = u->warm_start_mu_init > 0 ? u->warm_start_mu_init : 0.01;
     c.bound_relax = u->bound_relax_factor >= 0 ? u->bound_relax_factor : 1e-8;
     c.bound_push = u->bound_push > 0 ? u->bound_push : 0.01;
     c.inf_bound = u->infinity > 0 ? u->infinity : 1e19;

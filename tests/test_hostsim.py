@@ -22,7 +22,7 @@ class DevConfig(C.Structure):
     _fields_ = [("N", C.c_int), ("dT", C.c_double), ("w_com", C.c_double * 3), ("w_h", C.c_double), ("w_pos", C.c_double),
                 ("w_sym", C.c_double), ("w_rate", C.c_double * 3), ("corner", C.c_double * 24), ("fricA", C.c_double * 12),
                 ("tol", C.c_double), ("max_iter", C.c_int), ("mu_init", C.c_double), ("bound_relax", C.c_double),
-                ("bound_push", C.c_double), ("inf_bound", C.c_double), ("pc", C.c_int)]
+                ("bound_push", C.c_double), ("inf_bound", C.c_double), ("pc", C.c_int), ("mu_warm", C.c_double)]
 
 
 @pytest.fixture(scope="module")
@@ -49,6 +49,7 @@ def dev_config(N, tol=1e-8, pc=0, **kw):
     c.fricA[:] = np.asarray(Oracle().friction_matrix(o.mu), dtype=np.float64).reshape(-1).tolist()
     c.tol, c.max_iter, c.mu_init, c.bound_relax, c.bound_push, c.inf_bound = tol, 200, 0.1, 1e-8, 0.01, 1e19
     c.pc = pc
+    c.mu_warm = 0.01
     return c, o
 
 
