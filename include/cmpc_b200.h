@@ -17,6 +17,10 @@
  * success or a negative CMPC_E_* code; they never throw and never fall back to a CPU path.
  *
  * Thread safety: calls on different handles are independent; a handle must not be used from two threads at once.
+ * Stream semantics: a handle owns ONE work queue and ONE scratch arena, so it has at most one solve in flight: solves
+ * enqueued on different streams are serialised by the library (an event recorded behind every solve; a solve on another
+ * stream than the previous one waits for it on the device).  Use one handle per stream to overlap solves.  Every entry
+ * point runs on the handle's device and restores the caller's current device before it returns.
  */
 #ifndef CMPC_B200_H
 #define CMPC_B200_H

@@ -1,6 +1,6 @@
 // cmpc_ipm.cuh -- the interior-point solve of one centroidal-MPC instance by one team of NT threads, STAGE MAJOR.
 //
-// Same algorithm as ipm_solve() of cmpc_core.cuh (IPOPT's filter line-search interior point, Waechter & Biegler 2006, the
+// The algorithm (IPOPT's filter line-search interior point, Waechter & Biegler 2006, the
 // restatement of what BLF CentroidalMPC::advance() delegates to CasADi + IPOPT at
 // /root/reference/src/centroidal-mpc-walking/src/CentroidalMPCBlock.cpp:615), re-organised for the GPU:
 //   * every per-instance vector lives knot by knot (z_k = [s_k | u_k], the 15 equality rows that define s_k, the 38 path rows

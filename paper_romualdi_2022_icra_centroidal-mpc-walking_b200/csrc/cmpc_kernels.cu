@@ -402,6 +402,7 @@ struct cmpc_handle_s {
     int groups = 1;  // independent lock-step groups inside a CTA
     bool latency_path = false;  // default geometry: batches of at most one instance per SM go to the single-team kernel
     int device = 0, sm_count = 0, lockstep = 1, threads = CMPC_DEFAULT_TEAM, ctas_per_sm = 0, grid = 0, smem = 0;
+    int shift_smem = 0, eval_smem = 0;  // dynamic shared memory of the auxiliary kernels
     size_t work_stride = 0, work_slots = 0;
     double* d_work = nullptr;
     unsigned int* d_counter = nullptr;
@@ -414,7 +415,26 @@ struct cmpc_handle_s {
     int *d_status = nullptr, *d_iters = nullptr;
     long long launches = 0;
     int last_cuda = 0;
+    // a handle has ONE work queue and ONE scratch arena: solves on it are serialised on the device.  `done` is recorded
+    // behind every solve; a solve enqueued on another stream than the previous one waits for it first.
+    cudaEvent_t done = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool in_flight = false;
 };
+
+// every entry point runs on the handle's device and leaves the caller's current device as it found it
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int dev)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+        else if (err == cudaSuccess) prev = -1;  // nothing to restore
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define CMPC_ON_DEVICE(h) DeviceGuard guard_((h)->device); CK(guard_.err)
 
 #define CK(call)                                           \
     do {                                                   \
@@ -507,7 +527,8 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
     if (u->mu_strategy < 0 || u->mu_strategy > CMPC_MU_MEHROTRA) { delete h; return CMPC_E_INVALID; }
     c.pc = u->mu_strategy == CMPC_MU_MONOTONE ? 0 : 1;
     h->device = u->device;
-    cudaError_t e = cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
+    cudaError_t e = guard.err;
     cudaDeviceProp prop;
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, h->device);
     if (e != cudaSuccess) { delete h; return CMPC_E_CUDA; }
@@ -516,27 +537,42 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
     h->threads = u->threads_per_instance == 0 ? CMPC_DEFAULT_TEAM : u->threads_per_instance;
     h->lockstep = u->teams_per_cta == 0 ? (u->threads_per_instance == 0 ? CMPC_DEFAULT_LOCKSTEP : 1) : u->teams_per_cta;
     h->groups = u->lockstep_groups > 0 ? u->lockstep_groups : CMPC_DEFAULT_GROUPS;
-    if (const char* gs = getenv("CMPC_GROUPS")) h->groups = atoi(gs);  // experiments (profiles/r1_notes.md)
     if (h->groups < 1) h->groups = 1;
     if (h->groups > h->lockstep) h->groups = h->lockstep;
     const void* kfn = team_kernel(h->threads, h->lockstep);
     if (!kfn) { delete h; return CMPC_E_INVALID; }
-    // small batches (at most one instance per SM) are latency bound: one team of 128 threads per CTA, no register cap
-    h->latency_path = u->threads_per_instance == 0 && u->teams_per_cta == 0 && !getenv("CMPC_NO_LATENCY_PATH");
+    // small batches (at most four instances per SM) are latency bound: one team of 128 threads per CTA (default geometry only)
+    h->latency_path = u->threads_per_instance == 0 && u->teams_per_cta == 0;
     h->smem = (int)sizeof(ISmem) * h->lockstep;
     int occ = 0;
     e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kfn, h->threads * h->lockstep, h->smem);
     if (e != cudaSuccess || occ < 1) { h->last_cuda = (int)e; delete h; return CMPC_E_CUDA; }
     h->ctas_per_sm = (u->ctas_per_sm > 0 && u->ctas_per_sm < occ) ? u->ctas_per_sm : occ;
-    if (h->ctas_per_sm < occ) {  // fewer resident teams than fit: give the rest of the shared-memory carve-out back to L1
-        int pct = (int)((100.0 * h->ctas_per_sm * (h->smem + 1024)) / (228.0 * 1024.0)) + 1;
-        if (pct > 100) pct = 100;
-        cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    // Function attributes are per device, not per handle, so they are set HERE, once, to values that depend on nothing but
+    // the kernel: every handle writes the same numbers and no solve call touches them.
+    //  * carve-out of the single-team kernels: what their resident CTAs need (2 x / 4 x (ISmem + 1 KB)), the rest of the
+    //    256 KB stays L1 behind the scratch vectors and the spills (a lone team is 10 % faster than with the carve-out at its
+    //    maximum, profiles/r1_notes.md)
+    //  * the auxiliary kernels take 8 (53 N + 15) / 8 (40 N + 64) bytes of dynamic shared memory: opt in above 48 KB
+    {
+        auto pct = [](int ctas) { int v = (int)((100.0 * ctas * (sizeof(ISmem) + 1024)) / (228.0 * 1024.0)) + 1; return v > 100 ? 100 : v; };
+        if (h->ctas_per_sm < occ) e = cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, pct(h->ctas_per_sm * h->lockstep));
+        if (e == cudaSuccess && h->latency_path) {
+            e = cudaFuncSetAttribute((const void*)cmpc_solve_team_kernel<128, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ISmem));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)cmpc_solve_team_kernel<128, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ISmem));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)cmpc_solve_team_kernel<128, 1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct(2));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)cmpc_solve_team_kernel<128, 1, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct(4));
+        }
+        h->shift_smem = (int)(sizeof(double) * dim_g(c.N));
+        h->eval_smem = (int)(sizeof(double) * (c.N * SD_STRIDE + 64));
+        if (e == cudaSuccess && h->shift_smem > 48 * 1024) e = cudaFuncSetAttribute((const void*)cmpc_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->shift_smem);
+        if (e == cudaSuccess && h->eval_smem > 48 * 1024) e = cudaFuncSetAttribute((const void*)cmpc_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->eval_smem);
+        if (e != cudaSuccess) { h->last_cuda = (int)e; delete h; return CMPC_E_CUDA; }
     }
     h->grid = h->sm_count * h->ctas_per_sm;  // persistent grid: a multiple of the SM count
     h->work_stride = ((size_t)works_doubles(c.N) + 15) & ~(size_t)15;
-    h->work_slots = (size_t)h->grid * h->lockstep;
+    h->work_slots = std::max((size_t)h->grid * h->lockstep, h->latency_path ? (size_t)4 * h->sm_count : (size_t)0);
     Csc jc, hc;
     build_csc(c.N, false, jc);
     build_csc(c.N, true, hc);
@@ -549,14 +585,14 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
         cmpc_destroy(h);
         return CMPC_E_ALLOC;
     }
-    cudaMemset(h->d_work, 0, sizeof(double) * h->work_stride * h->work_slots);
-    {
-        std::vector<unsigned short> cm(CF_DINV);
-        build_cmap(cm.data());
-        cudaMemcpy(h->d_cmap, cm.data(), sizeof(unsigned short) * CF_DINV, cudaMemcpyHostToDevice);
-    }
-    cudaMemcpy(h->d_jslot, jc.slot.data(), sizeof(int) * jc.slot.size(), cudaMemcpyHostToDevice);
-    cudaMemcpy(h->d_hslot, hc.slot.data(), sizeof(int) * hc.slot.size(), cudaMemcpyHostToDevice);
+    std::vector<unsigned short> cm(CF_DINV);
+    build_cmap(cm.data());
+    e = cudaMemset(h->d_work, 0, sizeof(double) * h->work_stride * h->work_slots);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_cmap, cm.data(), sizeof(unsigned short) * CF_DINV, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_jslot, jc.slot.data(), sizeof(int) * jc.slot.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_hslot, hc.slot.data(), sizeof(int) * hc.slot.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming);
+    if (e != cudaSuccess) { cmpc_destroy(h); return CMPC_E_CUDA; }
     *out = h;
     return CMPC_OK;
 }
@@ -564,10 +600,14 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
 int cmpc_destroy(cmpc_handle h)
 {
     if (!h) return CMPC_E_INVALID;
-    cudaSetDevice(h->device);
-    cudaFree(h->d_work); cudaFree(h->d_counter); cudaFree(h->d_jslot); cudaFree(h->d_hslot); cudaFree(h->d_gscratch); cudaFree(h->d_cmap);
-    cudaFree(h->d_p); cudaFree(h->d_lbg); cudaFree(h->d_ubg); cudaFree(h->d_x); cudaFree(h->d_lam); cudaFree(h->d_obj);
-    cudaFree(h->d_status); cudaFree(h->d_iters);
+    {
+        DeviceGuard guard(h->device);
+        if (h->in_flight && h->done) cudaEventSynchronize(h->done);  // the scratch arena must outlive the last solve
+        if (h->done) cudaEventDestroy(h->done);
+        cudaFree(h->d_work); cudaFree(h->d_counter); cudaFree(h->d_jslot); cudaFree(h->d_hslot); cudaFree(h->d_gscratch); cudaFree(h->d_cmap);
+        cudaFree(h->d_p); cudaFree(h->d_lbg); cudaFree(h->d_ubg); cudaFree(h->d_x); cudaFree(h->d_lam); cudaFree(h->d_obj);
+        cudaFree(h->d_status); cudaFree(h->d_iters);
+    }
     delete h;
     return CMPC_OK;
 }
@@ -579,45 +619,38 @@ int cmpc_solve_batched(cmpc_handle h, int batch, const double* d_p, const double
     if (!h || batch < 0 || !d_p || !d_lbg || !d_ubg || !d_x) return CMPC_E_INVALID;
     if (batch == 0) return CMPC_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    CK(cudaSetDevice(h->device));
+    CMPC_ON_DEVICE(h);
+    // one work queue and one scratch arena per handle: a solve on another stream than the previous one is ordered behind it
+    if (h->in_flight && st != h->last_stream) CK(cudaStreamWaitEvent(st, h->done, 0));
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
     // small batches are latency bound: independent single-team CTAs of 128 threads (no lock-step, no 80-register cap) beat the
     // seven-team CTAs while at most four of them share an SM (profiles/r1_notes.md): up to 2 per SM the kernel compiled
     // without a register cap (254 registers, two CTAs run as fast as one), up to 4 per SM the one compiled for 4 CTAs (128)
-    // (CMPC_SINGLE_TEAM_PERSIST=1, experiments only: four single-team CTAs per SM for every batch size: 59 solves/ms against 69)
-    const bool st_persist = getenv("CMPC_SINGLE_TEAM_PERSIST") != nullptr;
-    if (h->latency_path && (size_t)4 * h->sm_count <= h->work_slots && (batch <= 4 * h->sm_count || st_persist)) {
-        // shared-memory carve-out: just what the resident CTAs need, the rest of the 256 KB stays L1 (a lone team is 10 % faster
-        // with L1 behind its scratch vectors and spills than with the carve-out at its maximum)
-        const int lgrid = std::min(batch, 4 * h->sm_count);
-        const int per_sm = (lgrid + h->sm_count - 1) / h->sm_count;
-        int pct = (int)((100.0 * per_sm * (sizeof(ISmem) + 1024)) / (228.0 * 1024.0)) + 1;
-        if (pct > 100) pct = 100;
-        if (per_sm <= 2) {
-            cudaFuncSetAttribute((const void*)cmpc_solve_team_kernel<128, 1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            cmpc_solve_team_kernel<128, 1, 1><<<lgrid, 128, (int)sizeof(ISmem), st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj,
+    if (h->latency_path && batch <= 4 * h->sm_count) {
+        const int per_sm = (batch + h->sm_count - 1) / h->sm_count;
+        if (per_sm <= 2)
+            cmpc_solve_team_kernel<128, 1, 1><<<batch, 128, (int)sizeof(ISmem), st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj,
                                                                                      d_status, d_iters, warm_duals, h->d_work,
                                                                                      h->work_stride, h->d_counter, h->d_cmap, 1);
-        } else {
-            cudaFuncSetAttribute((const void*)cmpc_solve_team_kernel<128, 1, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            cmpc_solve_team_kernel<128, 1, 4><<<lgrid, 128, (int)sizeof(ISmem), st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj,
+        else
+            cmpc_solve_team_kernel<128, 1, 4><<<batch, 128, (int)sizeof(ISmem), st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj,
                                                                                      d_status, d_iters, warm_duals, h->d_work,
                                                                                      h->work_stride, h->d_counter, h->d_cmap, 1);
-        }
-        h->launches++;
-        CK(cudaGetLastError());
-        return CMPC_OK;
-    }
-    int grid = std::min(batch, h->grid);  // a small batch is spread over the SMs (static first instance: team * grid + CTA)
+    } else {
+        int grid = std::min(batch, h->grid);  // a small batch is spread over the SMs (static first instance: team * grid + CTA)
 #define X(NT, G, C)                                                                                                      \
     if (h->threads == NT && h->lockstep == G)                                                                            \
         cmpc_solve_team_kernel<NT, G, C><<<grid, NT * G, h->smem, st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj, \
                                                                         d_status, d_iters, warm_duals, h->d_work,         \
                                                                         h->work_stride, h->d_counter, h->d_cmap, h->groups);
-    CMPC_FOR_EACH_KERNEL(X)
+        CMPC_FOR_EACH_KERNEL(X)
 #undef X
+    }
     h->launches++;
     CK(cudaGetLastError());
+    CK(cudaEventRecord(h->done, st));
+    h->last_stream = st;
+    h->in_flight = true;
     return CMPC_OK;
 }
 
@@ -625,15 +658,23 @@ static int ensure_host_staging(cmpc_handle h, int batch)
 {
     if (batch <= h->host_cap) return CMPC_OK;
     const int N = h->cfg.N;
+    if (h->in_flight) cudaEventSynchronize(h->done);  // a solve in flight may still read the old buffers
     cudaFree(h->d_p); cudaFree(h->d_lbg); cudaFree(h->d_ubg); cudaFree(h->d_x); cudaFree(h->d_lam); cudaFree(h->d_obj);
     cudaFree(h->d_status); cudaFree(h->d_iters);
+    h->d_p = h->d_lbg = h->d_ubg = h->d_x = h->d_lam = h->d_obj = nullptr;
+    h->d_status = h->d_iters = nullptr;
     h->host_cap = 0;
     size_t b = (size_t)batch;
     if (cudaMalloc(&h->d_p, 8 * b * dim_p(N)) != cudaSuccess || cudaMalloc(&h->d_lbg, 8 * b * dim_g(N)) != cudaSuccess ||
         cudaMalloc(&h->d_ubg, 8 * b * dim_g(N)) != cudaSuccess || cudaMalloc(&h->d_x, 8 * b * dim_x(N)) != cudaSuccess ||
         cudaMalloc(&h->d_lam, 8 * b * dim_g(N)) != cudaSuccess || cudaMalloc(&h->d_obj, 8 * b) != cudaSuccess ||
-        cudaMalloc(&h->d_status, 4 * b) != cudaSuccess || cudaMalloc(&h->d_iters, 4 * b) != cudaSuccess)
+        cudaMalloc(&h->d_status, 4 * b) != cudaSuccess || cudaMalloc(&h->d_iters, 4 * b) != cudaSuccess) {
+        cudaFree(h->d_p); cudaFree(h->d_lbg); cudaFree(h->d_ubg); cudaFree(h->d_x); cudaFree(h->d_lam); cudaFree(h->d_obj);
+        cudaFree(h->d_status); cudaFree(h->d_iters);
+        h->d_p = h->d_lbg = h->d_ubg = h->d_x = h->d_lam = h->d_obj = nullptr;
+        h->d_status = h->d_iters = nullptr;
         return CMPC_E_ALLOC;
+    }
     h->host_cap = batch;
     return CMPC_OK;
 }
@@ -643,7 +684,7 @@ int cmpc_solve_host(cmpc_handle h, int batch, const double* p, const double* lbg
 {
     if (!h || batch < 0 || !p || !lbg || !ubg || !x) return CMPC_E_INVALID;
     if (batch == 0) return CMPC_OK;
-    CK(cudaSetDevice(h->device));
+    CMPC_ON_DEVICE(h);
     int rc = ensure_host_staging(h, batch);
     if (rc) return rc;
     const int N = h->cfg.N;
@@ -669,11 +710,10 @@ int cmpc_shift_warmstart(cmpc_handle h, int batch, double* d_x, double* d_lam_g,
 {
     if (!h || batch < 0 || !d_x) return CMPC_E_INVALID;
     if (batch == 0) return CMPC_OK;
-    CK(cudaSetDevice(h->device));
+    CMPC_ON_DEVICE(h);
     const int N = h->cfg.N;
     int grid = std::min(batch, h->sm_count * 8);
-    size_t smem = sizeof(double) * dim_g(N);
-    cmpc_shift_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(N, batch, d_x, d_lam_g);
+    cmpc_shift_kernel<<<grid, 256, h->shift_smem, (cudaStream_t)stream>>>(N, batch, d_x, d_lam_g);
     h->launches++;
     CK(cudaGetLastError());
     return CMPC_OK;
@@ -689,13 +729,12 @@ int cmpc_eval_jac_fg(cmpc_handle h, int batch, const double* d_x, const double* 
 {
     if (!h || batch < 0 || !d_x || !d_p) return CMPC_E_INVALID;
     if (batch == 0) return CMPC_OK;
-    CK(cudaSetDevice(h->device));
+    CMPC_ON_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     const int N = h->cfg.N;
     if (d_f || d_grad || d_g) {
         int grid = std::min(batch, h->sm_count * 4);
-        size_t smem = sizeof(double) * (N * SD_STRIDE + 64);
-        cmpc_eval_kernel<<<grid, 128, smem, st>>>(h->cfg, batch, d_x, d_p, d_f, d_grad, d_g, h->d_gscratch);
+        cmpc_eval_kernel<<<grid, 128, h->eval_smem, st>>>(h->cfg, batch, d_x, d_p, d_f, d_grad, d_g, h->d_gscratch);
         h->launches++;
         CK(cudaGetLastError());
     }
@@ -715,7 +754,7 @@ int cmpc_eval_hess_l(cmpc_handle h, int batch, const double* d_x, const double* 
     (void)d_x;  // the hessian of the lagrangian does not depend on x
     if (!h || batch < 0 || !d_p || !d_lam_g || !d_hess) return CMPC_E_INVALID;
     if (batch == 0) return CMPC_OK;
-    CK(cudaSetDevice(h->device));
+    CMPC_ON_DEVICE(h);
     const int N = h->cfg.N;
     long long total = (long long)batch * nnz_hess(N);
     int grid = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16);
@@ -730,7 +769,7 @@ int cmpc_rollout_plant(cmpc_handle h, int batch, const double* d_x, const double
 {
     if (!h || batch < 0 || !d_x || !d_p || !d_state || substeps < 0) return CMPC_E_INVALID;
     if (batch == 0) return CMPC_OK;
-    CK(cudaSetDevice(h->device));
+    CMPC_ON_DEVICE(h);
     int grid = std::min((batch + 127) / 128, h->sm_count * 8);
     cmpc_plant_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(h->cfg, batch, d_x, d_p, d_ext, d_state, dt, substeps);
     h->launches++;
@@ -741,24 +780,26 @@ int cmpc_rollout_plant(cmpc_handle h, int batch, const double* d_x, const double
 int cmpc_measure_fp64_peak(cmpc_handle h, double* tflops)
 {
     if (!h || !tflops) return CMPC_E_INVALID;
-    CK(cudaSetDevice(h->device));
+    CMPC_ON_DEVICE(h);
     const int iters = 1 << 16, threads = 256, blocks = h->sm_count * 8;
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
     double best = 0.0;
-    for (int rep = 0; rep < 4; ++rep) {  // first repetition is the warm-up
-        CK(cudaEventRecord(e0, 0));
+    for (int rep = 0; e == cudaSuccess && rep < 4; ++rep) {  // first repetition is the warm-up
+        e = cudaEventRecord(e0, 0);
         cmpc_dfma_probe_kernel<<<blocks, threads>>>(h->d_gscratch, iters, 0.999999, 1e-9);
-        CK(cudaEventRecord(e1, 0));
-        CK(cudaEventSynchronize(e1));
+        if (e == cudaSuccess) e = cudaEventRecord(e1, 0);
+        if (e == cudaSuccess) e = cudaEventSynchronize(e1);
         float ms = 0;
-        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (e != cudaSuccess) break;
         const double tf = 2.0 * 8.0 * iters * (double)threads * blocks / (ms * 1e-3) / 1e12;
         if (rep > 0 && tf > best) best = tf;
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    CK(e);
     *tflops = best;
     return CMPC_OK;
 }

@@ -1,6 +1,6 @@
 """Launch time of small and mid-size batches (iCub3, N = 15, cold start) with the default dispatch: up to 2 / up to 4 instances per
-SM on independent single-team CTAs, larger batches on the seven-team lock-step CTAs (CMPC_NO_LATENCY_PATH=1 forces the latter,
-CMPC_SINGLE_TEAM_PERSIST=1 the former for every size).  usage: [CMPC_B200_LIB=...] python profiles/lat_sweep.py B1 B2 ..."""
+SM on independent single-team CTAs, larger batches on the seven-team lock-step CTAs (round 1 switched between the two with environment variables;
+the library no longer reads the environment: force the seven-team kernel with teams_per_cta = 7).  usage: [CMPC_B200_LIB=...] python profiles/lat_sweep.py B1 B2 ..."""
 import importlib, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

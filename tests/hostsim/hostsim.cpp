@@ -1,4 +1,5 @@
-// tests/hostsim/hostsim.cpp -- TEST-ONLY single-thread build of the CUDA solver source (csrc/cmpc_core.cuh).
+// tests/hostsim/hostsim.cpp -- TEST-ONLY host build of the CUDA solver source (csrc/cmpc_ipm.cuh, csrc/cmpc_warp.cuh with emulated
+// lanes) next to the first-generation generic formulation (cmpc_generic.cuh, an independent second implementation).
 //
 // There is no GPU in the development container, so the solver's math is debugged by compiling the very same
 // __host__ __device__ source with a one-thread "CTA".  This library is built and loaded ONLY by
@@ -8,6 +9,7 @@
 #include <vector>
 
 #include "../../paper_romualdi_2022_icra_centroidal-mpc-walking_b200/csrc/cmpc_ipm.cuh"
+#include "cmpc_generic.cuh"
 
 namespace {
 struct HostCta {

@@ -29,7 +29,7 @@ class DevConfig(C.Structure):
 def hostsim():
     src = os.path.join(HS, "hostsim.cpp")
     lib = os.path.join(HS, "libhostsim.so")
-    deps = [src] + [os.path.join(ROOT, pkg().__name__, "csrc", f) for f in ("cmpc_core.cuh", "cmpc_warp.cuh", "cmpc_ipm.cuh", "cmpc_layout.cuh")]
+    deps = [src, os.path.join(HS, "cmpc_generic.cuh")] + [os.path.join(ROOT, pkg().__name__, "csrc", f) for f in ("cmpc_core.cuh", "cmpc_warp.cuh", "cmpc_ipm.cuh", "cmpc_layout.cuh")]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", src, "-o", lib], check=True)
     L = C.CDLL(lib)
