@@ -14,6 +14,10 @@ ipopt_tolerance of the workload's robot ini (iCub3: 1e-8; ergoCubGazeboV1_1: 1e-
   roofline : executed FP64 flop / kernel time against the measured FP64 FMA peak (the kernel is FP64 CUDA-core
              bound; HBM numbers are given beside it to show that HBM is not the bound)
   cpu_baseline : the CPU oracle (restatement of the IPOPT solve) on the host cores, bounded sample, rank 0, N = 1 only
+  north_star_configs : BASELINE.json configs[2] (65536 ergoCub instances in total, STRONG-scaled over the ranks, at tol 1e-8 and
+             at the ini's 1e-4) and configs[3] (4096 closed-loop rollouts x 100 ticks in total), measured in the same run
+  per_rank : kernel time and iteration statistics of every rank (the solve needs no exchange; ONE all_gather of the
+             per-instance results ends the timed region)
 --impl reference times the reference's CPU path (the oracle port: IPOPT/CasADi are not installable here).
 """
 from __future__ import annotations
@@ -33,15 +37,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 PKG = "paper_romualdi_2022_icra_centroidal-mpc-walking_b200"
 
-# FP64 flop executed per interior-point iteration and knot by cmpc_solve_kernel (measured with ncu, see
-# profiles/ and DESIGN.md "flop accounting"), and the canonical dense figure of SURVEY.md 8(d)
-# (ncu smsp__sass_thread_inst_executed_op_{dfma x 2, dadd, dmul}_pred_on of one launch / (iterations x knots): captures prof_t96c
-# (monotone) and prof_pc2 (predictor-corrector: its second solve is two matrix-vector sweeps, few flops, and the monotone figure
-# contains the refinement sweeps that the corrector replaces))
+# FP64 flop executed per interior-point iteration and knot by cmpc_solve_team_kernel (ncu
+# smsp__sass_thread_inst_executed_op_{dfma x 2, dadd, dmul}_pred_on of one launch / (iterations x knots), see profiles/ and
+# DESIGN.md "flop accounting"; the per-iteration-and-knot work does not depend on the workload: the same code runs for every
+# robot, horizon and batch), and the canonical dense figure of SURVEY.md 8(d)
 FLOP_EXEC_PER_ITER_KNOT = {"monotone": 1.22e5, "mehrotra": 1.19e5}
 FLOP_CANON_PER_ITER_KNOT = 422275.0
-# bytes per launch of icub3_b1024 (team 96, 7 teams / CTA in 3 groups): ncu captures prof_g3 (monotone), prof_pc2 (predictor-corrector)
-DRAM_TRAFFIC_PER_LAUNCH = {"monotone": 1.240e10, "mehrotra": 1.197e10}
+# measured DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum), keyed by (workload, batch, strategy)
+DRAM_TRAFFIC_PER_LAUNCH = {("icub3_b1024", 1024, "monotone"): 1.240e10, ("icub3_b1024", 1024, "mehrotra"): 1.197e10}
 # ipopt_tolerance of the robot ini each workload is built from (config/robots/<robot>/centroidal_mpc.ini)
 INI_TOLERANCE = {"icub3_b1024": 1e-8, "ergocub_b65536": 1e-4}
 FP64_PEAK_FALLBACK_TFLOPS = 37.0  # vendor figure (HGX B200 296 TF / 8); used only if the live DFMA probe fails
@@ -60,6 +63,13 @@ def workload(name: str, pkg, wl, seed: int, batch: int = 0):
     else:
         raise SystemExit(f"unknown workload {name}")
     return cfg, w, ocfg
+
+
+def config_dict(name: str, B: int, N: int, tol: float):
+    """static description of the workload: the same dict on both arms (--impl ours / reference)"""
+    return {"workload": name, "instances_per_gpu": B, "horizon_knots": N, "ipopt_tolerance": tol,
+            "robot_ini": "iCubGazeboV3/centroidal_mpc.ini" if name.startswith("icub3") else "ergoCubGazeboV1_1/centroidal_mpc.ini",
+            "cold_start": True, "l2": "GPU arm: flushed between steps (256 MB write); CPU arm: not applicable"}
 
 
 class ClockSampler(threading.Thread):
@@ -114,7 +124,24 @@ def cpu_oracle_rate(ocfg, w, sample: int, threads: int, tol: float):
     return sample / dt, dt, ok, its
 
 
-def parity_report(x_gpu, obj_gpu, status_gpu, L):
+def foot_wrenches(L, x, p, corners):
+    """(B, N, 2, 6) per-foot resultant force and torque (about the foot origin) of the corner forces at every knot"""
+    B, N = x.shape[0], L.N
+    out = np.zeros((B, N, 2, 6))
+    cr = np.asarray(corners, dtype=np.float64)
+    for k in range(N):
+        for c in range(2):
+            R = p[:, L.p_rot(c, k):L.p_rot(c, k) + 9].reshape(B, 3, 3).transpose(0, 2, 1)
+            en = p[:, L.p_en(c, k)][:, None]
+            for j in range(4):
+                f = en * x[:, L.x_frc(c, j, k):L.x_frc(c, j, k) + 3]
+                arm = R @ cr[j]
+                out[:, k, c, :3] += f
+                out[:, k, c, 3:] += np.cross(arm, f)
+    return out
+
+
+def parity_report(x_gpu, obj_gpu, status_gpu, L, p, corners):
     """north_star: "the fraction of instances landing in the same local optimum is reported" -- GPU solutions of the timed
     workload (default barrier update) against the oracle's solutions of the same instances (IPOPT's default path)."""
     xo, obj_o, st_o = cpu_oracle_rate.last
@@ -127,10 +154,16 @@ def parity_report(x_gpu, obj_gpu, status_gpu, L):
     xg = x_gpu[:n]
     d_obj = np.abs(obj_gpu[:n] - obj_o) / np.maximum(1.0, np.abs(obj_o))
     same_state = both & (d_obj <= 1e-6) & (rel(xg[:, st], xo[:, st]) <= 1e-5) & (rel(xg[:, fs], xo[:, fs]) <= 1e-5)
+    wg, wo = foot_wrenches(L, xg, p[:n], corners).reshape(n, -1), foot_wrenches(L, xo, p[:n], corners).reshape(n, -1)
+    same_wrench = same_state & (rel(wg, wo) <= 1e-5)
     same_all = same_state & (rel(xg[:, frc], xo[:, frc]) <= 1e-5)
     return {"instances": int(n), "both_converged": int(both.sum()),
-            "same_objective_trajectories_footsteps": int(same_state.sum()), "same_corner_forces_too": int(same_all.sum()),
+            "same_objective_trajectories_footsteps": int(same_state.sum()),
+            "same_per_foot_wrenches_too": int(same_wrench.sum()), "same_corner_forces_too": int(same_all.sum()),
             "tolerances": "objective 1e-6 relative, scaled inf-norm 1e-5", "against": "oracle, IPOPT's default (monotone) path",
+            "note": "per-foot wrench = resultant force and torque of a foot's four corner forces at every knot (what the dynamics "
+                    "and the reference's whole-body layer see); with contact_force_symmetry_weight 0 (iCub3) the split over the "
+                    "corners is not unique",
             "max_rel_objective_difference": float(d_obj[both].max()) if both.any() else None}
 
 
@@ -140,7 +173,6 @@ def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     pkg_wl = importlib.import_module(PKG + ".workloads")
-    lay = importlib.import_module(PKG + ".layout")  # noqa: F841
 
     class _P:  # config factory without touching the CUDA library
         @staticmethod
@@ -163,12 +195,164 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "batched centroidal-MPC solves/sec", "value": value, "unit": "solves/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "note": "each step = bounded sample of the workload"},
+            "config": config_dict(args.workload, w["p"].shape[0], ocfg["N"], args.tol),
+            "solve_stats": {"mu_strategy": "monotone (IPOPT's default)", "converged": f"{ok}/{sample}", "mean_iterations": its,
+                            "note": "each step = bounded sample of the workload (the first instances)"},
             "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port",
                              "sample": f"{sample} instances of {args.workload} per step, tol {args.tol:g}, "
-                                       f"{ok}/{sample} converged, mean {its:.1f} iterations, tol {args.tol:g}"},
+                                       f"{ok}/{sample} converged, mean {its:.1f} iterations"},
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def max_over_ranks(v: float, dev, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([v], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(vals, dev, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().tolist()
+
+
+def run_config3(pkg, wl, dev, local, rank, world, flush, total=65536):
+    """BASELINE configs[2]: 65536 ergoCub instances (step adjustment and friction cones active, state noise x 2, footstep yaw
+    +-0.3) STRONG-scaled: rank r solves total / world of them.  Device-resident and end-to-end (cmpc_solve_host from pinned
+    host buffers) solves/s at tol 1e-8 and at the ini's ipopt_tolerance 1e-4."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+    B = total // world
+    w = wl.walk_batch(N=12, dT=0.1, B=B, seed=1000 + rank, state_noise=2.0, yaw_range=0.3, step_adjust=True)
+    tens = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+    d_p, d_lbg, d_ubg, d_x0 = tens(w["p"]), tens(w["lbg"]), tens(w["ubg"]), tens(w["x0"])
+    d_x = d_x0.clone()
+    h_p, h_lbg, h_ubg, h_x0 = pin(w["p"]), pin(w["lbg"]), pin(w["ubg"]), pin(w["x0"])
+    m = d_lbg.shape[1]
+    d_lam = torch.zeros(B, m, dtype=torch.float64, device=dev)
+    h_lam = torch.zeros(B, m, dtype=torch.float64).pin_memory()
+    h_obj = torch.zeros(B, dtype=torch.float64).pin_memory()
+    h_st, h_it = torch.zeros(B, dtype=torch.int32).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory()
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    out = {"workload": "ergocub_b65536", "instances_total": B * world, "instances_per_gpu": B, "scaling": "strong",
+           "horizon_knots": 12, "robot_ini": "ergoCubGazeboV1_1/centroidal_mpc.ini", "steps": 2, "warmup": 1}
+    for tol in (1e-8, 1e-4):
+        cfg = pkg.ergocub_config()
+        cfg.device, cfg.ipopt_tolerance = local, tol
+        solver = pkg.BatchedCentroidalMPC(cfg)
+        ev = []
+        for s in range(3):
+            flush.zero_()
+            d_x.copy_(d_x0)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if s == 1:
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+            a.record()
+            obj, status, iters, _ = solver.solve(d_p, d_lbg, d_ubg, d_x, d_lam)
+            b.record()
+            if s >= 1:
+                ev.append((a, b))
+        torch.cuda.synchronize()
+        t_own = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+        t_dev = max_over_ranks(t_own, dev, world)
+        st_h, it_h = status.cpu().numpy(), iters.cpu().numpy()
+        # end to end: the C-ABI call with pinned host buffers (H2D + solve + D2H + synchronisation inside the timed region)
+        h_xs = [h_x0.clone().pin_memory() for _ in range(3)]
+        solver.lib.cmpc_solve_host(solver.handle, B, vp(h_p), vp(h_lbg), vp(h_ubg), vp(h_xs[0]), vp(h_lam), vp(h_obj), vp(h_st), vp(h_it), 0)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for j in (1, 2):
+            rc = solver.lib.cmpc_solve_host(solver.handle, B, vp(h_p), vp(h_lbg), vp(h_ubg), vp(h_xs[j]), vp(h_lam), vp(h_obj), vp(h_st),
+                                            vp(h_it), 0)
+            assert rc == 0, rc
+        t_e2e = max_over_ranks(time.perf_counter() - t0, dev, world)
+        conv, it_sum = sum_over_ranks([float((st_h == 0).sum()), float(it_h.sum())], dev, world)
+        it_max = max_over_ranks(float(it_h.max()), dev, world)
+        out[f"tol_{tol:g}"] = {"solves_per_s": world * B * len(ev) / t_dev, "ms_per_step": 1e3 * t_dev / len(ev),
+                               "e2e_solves_per_s": world * B * 2 / t_e2e, "converged": f"{int(conv)}/{B * world}",
+                               "mean_iterations": it_sum / (B * world), "max_iterations": int(it_max),
+                               "kernel_ms_this_rank": 1e3 * t_own / len(ev)}
+        solver.close()
+    return out
+
+
+def run_config4(pkg, dev, local, rank, world, total=4096, ticks=100):
+    """BASELINE configs[3]: 4096 closed-loop rollouts (10 s of walking = 100 MPC ticks, one push per rollout, warm-started shift
+    every tick) in total, rank r rolls out total / world of them; no exchange during the rollouts, ONE gather at the end."""
+    import torch
+    import torch.distributed as dist
+    R = importlib.import_module(PKG + ".rollout")
+    sharding = importlib.import_module(PKG + ".sharding")
+    B = total // world
+    out = {"rollouts_total": B * world, "rollouts_per_gpu": B, "ticks": ticks, "scaling": "strong", "robot_ini": "ergoCubGazeboV1_1/centroidal_mpc.ini"}
+    for tol in (1e-4, 1e-8):
+        cfg = pkg.ergocub_config()
+        cfg.device, cfg.ipopt_tolerance = local, tol
+        solver = pkg.BatchedCentroidalMPC(cfg)
+        R.closed_loop_rollout(solver, B=B, ticks=4, seed=rank)          # warm-up (allocator, kernels, tables)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        res = R.closed_loop_rollout(solver, B=B, ticks=ticks, seed=100 + rank, time_device=True)
+        local_stats = torch.from_numpy(np.stack([res["converged_ticks"], res["iterations"]], axis=1).astype(np.float64)).to(dev)
+        allres = sharding.gather_results(local_stats, world)
+        torch.cuda.synchronize()
+        wall = max_over_ranks(time.perf_counter() - t0, dev, world)
+        t_dev = max_over_ranks(res["device_ms"] * 1e-3, dev, world)
+        allres = allres.cpu().numpy()
+        n = B * world
+        out[f"tol_{tol:g}"] = {"mpc_ticks_per_s_device": n * ticks / t_dev, "mpc_ticks_per_s_wall": n * ticks / wall,
+                               "wall_s": wall, "device_s": t_dev, "converged_ticks": f"{int(allres[:, 0].sum())}/{n * ticks}",
+                               "iterations_per_tick": float(allres[:, 1].sum() / (n * ticks))}
+        solver.close()
+    return out
+
+
+def host_operator_latency(samples=24):
+    """BASELINE configs[0] through the drop-in class: one CentroidalMPC object initialised from the iCub3 ini, straight-walk
+    contact list, cold start every tick (the ini does not enable the warm start): wall time of advance() = input population,
+    H2D, solve, D2H, output unpacking."""
+    H = importlib.import_module(PKG + ".host")
+    wl = importlib.import_module(PKG + ".workloads")
+    lay = importlib.import_module(PKG + ".layout")
+    ini = os.path.join(ROOT, "tests", "data", "icub3", "centroidal_mpc_walking.ini")
+    m = H.CentroidalMPCHost(ini, "CENTROIDAL_MPC")
+    N, L = m.N, lay.Layout(m.N)
+    lists = H.walk_contact_lists(0, n_steps=8 + samples // 8)
+    lat, its = [], []
+    for j in range(samples + 3):
+        w = wl.walk_batch(N=N, dT=m.dT, B=1, seed=j, phase=j, state_noise=0.0, step_adjust=True)
+        p, g0 = w["p"][0], L.p_glob()
+        m.set_state(p[g0:g0 + 3], p[g0 + 3:g0 + 6], p[g0 + 6:g0 + 9])
+        m.set_reference_trajectory(p[L.p_comref(0):L.p_comref(0) + 3 * (N + 1)], p[L.p_href(0):L.p_href(0) + 3 * (N + 1)])
+        m.set_contact_phase_list(lists)
+        t0 = time.perf_counter()
+        ok = m.advance()
+        dt = time.perf_counter() - t0
+        if not ok:
+            return {"error": m.last_error()}
+        if j >= 3:
+            lat.append(1e3 * dt)
+            its.append(m.stats()[1])
+    m.close()
+    return {"p50_ms": float(np.median(lat)), "p95_ms": float(np.percentile(lat, 95)), "samples": len(lat),
+            "mean_iterations": float(np.mean(its)),
+            "api": "CentroidalMPC::advance() of the C++ drop-in class (iCub3 ini, straight-walk contact list, state on the reference, cold start)"}
 
 
 def main():
@@ -182,6 +366,10 @@ def main():
                     help="ipopt_tolerance; default = the value of the workload's robot ini (iCubGazeboV3: 1e-8, the BLF default, "
                          "its ini leaves the key commented out; ergoCubGazeboV1_1: 1e-4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the north-star configs 3 / 4 and the host-operator latency")
+    ap.add_argument("--gather", default="end", choices=["end", "per-step"],
+                    help="the one exchange of the sharded job: a single all_gather after the last step (default) or one per step on a "
+                         "side stream (round 1; kept for the A/B of DESIGN.md section 7)")
     ap.add_argument("--team", type=int, default=0, help="threads per instance (32/64/96/128), 0 = library default")
     ap.add_argument("--lockstep", type=int, default=0, help="teams per CTA walking in lock-step (1, 3, 7; 0 = library default)")
     ap.add_argument("--groups", type=int, default=0, help="independent lock-step groups per CTA (0 = library default)")
@@ -232,20 +420,25 @@ def main():
     d_lam = torch.zeros(B, m, dtype=torch.float64, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2
 
-    # the only exchange of the sharded job: gather per-instance results, overlapped with the next batch's
-    # solve on a side stream (sharding.AsyncGather): the ranks meet once, at the end of the timed region
-    gather = sharding.AsyncGather(world)
-
-    def step():
-        d_x.copy_(d_x0)
-        obj, status, iters, _ = solver.solve(d_p, d_lbg, d_ubg, d_x, d_lam)
-        gather.submit(sharding.pack_results(obj, status, iters))
-        return obj, status, iters
+    # The only exchange of the sharded job is the gather of the per-instance results.  Default: the results of
+    # every step stay on the device and ONE all_gather follows the last step ("once per batch / rollout"): no NCCL kernel is
+    # resident while a solve runs.  --gather per-step = round 1: one all_gather per step on a side stream; its kernel waits on
+    # the SMs for the slowest peer while the next solve's persistent CTAs (one per SM, 222 KB of shared memory each) want every
+    # SM: that was the unexplained 8-10 % of round 1's multi-GPU runs.
+    per_step = args.gather == "per-step"
+    gather = sharding.AsyncGather(world) if per_step else None
+    results = torch.zeros(args.steps, B, 3, dtype=torch.float64, device=dev)
 
     for _ in range(args.warmup):
         flush.zero_()
-        obj, status, iters = step()
-    gather.wait()
+        d_x.copy_(d_x0)
+        obj, status, iters, _ = solver.solve(d_p, d_lbg, d_ubg, d_x, d_lam)
+        if per_step:
+            gather.submit(sharding.pack_results(obj, status, iters))
+    if per_step:
+        gather.wait()
+    else:
+        sharding.gather_results(sharding.pack_results(obj, status, iters), world)   # NCCL communicator warm-up
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -265,29 +458,44 @@ def main():
         kev[s][0].record()
         obj, status, iters, _ = solver.solve(d_p, d_lbg, d_ubg, d_x, d_lam)
         kev[s][1].record()
-        gather.submit(sharding.pack_results(obj, status, iters))
+        if per_step:
+            gather.submit(sharding.pack_results(obj, status, iters))
+        else:
+            results[s] = sharding.pack_results(obj, status, iters)
         ev[s][1].record()
     tail = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     tail[0].record()
-    gathered = gather.wait()               # the timed region ends when every gather has landed
+    if per_step:
+        gathered = gather.wait()           # the timed region ends when every gather has landed
+        n_gathered = sum(g.shape[0] for g in gathered)
+    else:
+        gathered = sharding.gather_results(results.view(args.steps * B, 3), world)
+        n_gathered = gathered.shape[0]
     tail[1].record()
     torch.cuda.synchronize()
-    assert len(gathered) == args.steps and gathered[-1].shape[0] == world * B
+    assert n_gathered == args.steps * world * B
     if world > 1:
         dist.barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = solver.launch_count() - launches0
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    t_dev = (sum(a.elapsed_time(b) for a, b in ev) + tail[0].elapsed_time(tail[1])) * 1e-3
+    t_steps = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    t_dev = t_steps + tail[0].elapsed_time(tail[1]) * 1e-3
     t_kernel = sum(a.elapsed_time(b) for a, b in kev) * 1e-3
-    tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_max = float(tt.item())
+    t_max = max_over_ranks(t_dev, dev, world)
     status_h, iters_h = status.cpu().numpy(), iters.cpu().numpy()
     conv = int((status_h == 0).sum())
     total_iters = int(iters_h.sum())
+    # per-rank record: kernel time per launch, own steps without the final gather, iteration statistics
+    mine = torch.tensor([1e3 * t_kernel / args.steps, 1e3 * t_steps / args.steps, float(iters_h.mean()), float(iters_h.max()),
+                         float(conv)], dtype=torch.float64, device=dev)
+    if world > 1:
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        allr = torch.stack(allr).cpu().numpy()
+    else:
+        allr = mine.cpu().numpy()[None]
 
     # ---- single-solve latency (the second half of BASELINE.json's metric): batch of ONE instance, device resident, p50
     lat = []
@@ -333,17 +541,12 @@ def main():
     for j in range(k_e2e):
         e2e_step(h_xs[j])
     torch.cuda.synchronize()
-    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * k_e2e / float(te.item())
+    e2e_value = world * B * k_e2e / max_over_ranks(time.perf_counter() - t0, dev, world)
     h2d = 8 * B * (npar + 2 * m + n)
     d2h = 8 * B * (n + m + 1) + 8 * B
-
+    geometry = solver.geometry()
+    peak_tf, peak_src = FP64_PEAK_FALLBACK_TFLOPS, "fallback: vendor 37 TFLOP/s FP64 (no measured FP64 peak in MEASURED_PEAKS.json)"
     if rank == 0:
-        value = world * B * args.steps / t_max
-        # FP64 roofline of the solver kernel
-        peak_tf, peak_src = FP64_PEAK_FALLBACK_TFLOPS, "fallback: vendor 37 TFLOP/s FP64 (no measured FP64 peak in MEASURED_PEAKS.json)"
         try:
             mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
             hbm_peak = float(mp.get("hbm_gbs", 6551.0))
@@ -357,6 +560,21 @@ def main():
                 peak_src = "measured live: cmpc_measure_fp64_peak (8 independent DFMA chains/thread, 148x8 CTAs x 256 threads); ncu peak_sustained 9472 DFMA/clk = 37.2"
         except Exception:
             pass
+    solver.close()
+
+    # ---- the other north-star configurations, in the same run (every rank takes part)
+    extras = {}
+    if not args.no_extras:
+        extras["config3_ergocub_65536_sharded"] = run_config3(pkg, wl, dev, local, rank, world, flush)
+        extras["config4_closed_loop_4096x100"] = run_config4(pkg, dev, local, rank, world)
+        if rank == 0:
+            try:
+                extras["config1_single_solve_host_operator"] = host_operator_latency()
+            except Exception as e:  # the host operator library is optional for the headline number
+                extras["config1_single_solve_host_operator"] = {"error": repr(e)}
+
+    if rank == 0:
+        value = world * B * args.steps / t_max
         kernel_s = t_kernel / args.steps
         flop_exec = total_iters * N * FLOP_EXEC_PER_ITER_KNOT[args.mu_strategy]
         flop_canon = total_iters * N * FLOP_CANON_PER_ITER_KNOT
@@ -366,31 +584,35 @@ def main():
             "metric": "batched centroidal-MPC solves/sec", "value": value, "unit": "solves/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "instances_per_gpu": B, "horizon_knots": N, "ipopt_tolerance": args.tol,
-                       "mu_strategy": args.mu_strategy,
-                       "robot_ini": "iCubGazeboV3/centroidal_mpc.ini" if args.workload.startswith("icub3") else
-                                    "ergoCubGazeboV1_1/centroidal_mpc.ini",
-                       "cold_start": True, "l2": "flushed between steps (256 MB write)",
-                       "converged": f"{conv}/{B}", "mean_iterations": total_iters / B,
-                       "solver_grid": solver.geometry()},
+            "config": config_dict(args.workload, B, N, args.tol),
+            "solve_stats": {"mu_strategy": args.mu_strategy, "converged": f"{conv}/{B}", "mean_iterations": total_iters / B,
+                            "solver_grid": geometry, "result_gather": args.gather},
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": k_e2e, "api": "cmpc_solve_host (pinned host buffers)"},
             "gpu_launches": int(launches),
             "latency": {"p50_single_solve_ms": float(np.median(lat)) if lat else None,
                         "p95_single_solve_ms": float(np.percentile(lat, 95)) if lat else None, "samples": len(lat),
-                        "iterations": int(iters_h[0]), "note": "batch of one instance, device resident, cold start; batches of up to 4 instances per SM run on independent single-team CTAs (128 threads; up to 2 per SM without a register cap) unless a geometry is forced"},
+                        "iterations": int(iters_h[0]),
+                        "e2e_host_operator_ms": (extras.get("config1_single_solve_host_operator") or {}).get("p50_ms"),
+                        "note": "batch of one instance, device resident, cold start; batches of up to 4 instances per SM run on independent single-team CTAs (128 threads; up to 2 per SM without a register cap) unless a geometry is forced; e2e_host_operator_ms = CentroidalMPC::advance() of the drop-in class"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "traffic": DRAM_TRAFFIC_PER_LAUNCH[args.mu_strategy] if (args.workload == "icub3_b1024" and B == 1024) else None,
-                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu captures prof_pc2 / prof_g3 "
-                                         "(profiles/r1_notes.md): the solver's scratch (iterate vectors + Riccati factors of 1036 "
-                                         "resident teams) does not fit the 126 MB L2", "peak_source": peak_src, "kernel": "cmpc_solve_team_kernel",
+                         "traffic": DRAM_TRAFFIC_PER_LAUNCH.get((args.workload, B, args.mu_strategy)),
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu, profiles/); null where this "
+                                         "exact (workload, batch, strategy) has not been captured",
+                         "peak_source": peak_src, "kernel": "cmpc_solve_team_kernel",
                          "kernel_ms_per_launch": 1e3 * kernel_s, "flop_executed_per_launch": flop_exec,
+                         "flop_per_iteration_and_knot": FLOP_EXEC_PER_ITER_KNOT[args.mu_strategy],
                          "flop_canonical_dense_per_launch": flop_canon,
                          "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / kernel_s / 1e9,
                                  "peak_gbs": hbm_peak, "frac": alg_bytes / kernel_s / 1e9 / hbm_peak}},
+            "per_rank": {"kernel_ms_per_launch": [float(v) for v in allr[:, 0]], "own_ms_per_step": [float(v) for v in allr[:, 1]],
+                         "mean_iterations": [float(v) for v in allr[:, 2]], "max_iterations": [int(v) for v in allr[:, 3]],
+                         "converged": [int(v) for v in allr[:, 4]]},
             "clocks": sampler.summary(),
             "wall_s_timed_region": t_wall,
         }
+        if extras:
+            line["north_star_configs"] = extras
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             sample = min(B, max(64, 64 * cores))   # about 10-30 core-seconds of CPU work
@@ -398,7 +620,8 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": "solves/s", "cores": cores, "kind": "port",
                                     "sample": f"first {sample} instances of the workload, {dt:.1f} s, {ok}/{sample} "
                                               f"converged, mean {its:.1f} iterations (oracle = IPOPT restatement)"}
-            line["parity"] = parity_report(h_x.numpy(), h_obj.numpy(), h_st.numpy(), solver.L)
+            line["parity"] = parity_report(h_x.numpy(), h_obj.numpy(), h_st.numpy(), solver.L, w["p"], ocfg.get(
+                "corners", [[(0.08, 0.01, 0), (0.08, -0.01, 0), (-0.08, -0.01, 0), (-0.08, 0.01, 0)]] * 2)[0])
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -44,9 +44,13 @@ enum {
 enum {
     CMPC_STATUS_CONVERGED = 0,    /* scaled KKT error <= ipopt_tolerance (IPOPT "Optimal Solution Found")          */
     CMPC_STATUS_MAX_ITER = 1,     /* ipopt_max_iteration reached                                                     */
-    CMPC_STATUS_LINE_SEARCH = 2,  /* filter line search failed (IPOPT would enter restoration)                       */
+    CMPC_STATUS_LINE_SEARCH = 2,  /* filter line search failed at a point that is not acceptable (IPOPT would enter  */
+                                  /* its restoration phase, which is not restated)                                   */
     CMPC_STATUS_NUMERICAL = 3,    /* regularisation exhausted / non-finite step                                      */
-    CMPC_STATUS_BAD_INPUT = 4     /* NaN, lbg > ubg, or an initial-condition / dynamics row with lbg != ubg          */
+    CMPC_STATUS_BAD_INPUT = 4,    /* NaN, lbg > ubg, or an initial-condition / dynamics row with lbg != ubg          */
+    CMPC_STATUS_ACCEPTABLE = 5    /* IPOPT "Solved To Acceptable Level": acceptable_iter consecutive iterates within  */
+                                  /* acceptable_tol, or the algorithm could not continue from such a point; CasADi   */
+                                  /* reports it as success, so does the host operator                               */
 };
 
 /* Mirrors the keys BLF CentroidalMPC::initialize reads from centroidal_mpc.ini
@@ -76,7 +80,10 @@ typedef struct cmpc_config {
                                             /* 0 = default (3: groups of 3 + 2 + 2 teams)                              */
     int mu_strategy;                        /* barrier-parameter update of the interior-point solve:                     */
                                             /* CMPC_MU_DEFAULT (0) = CMPC_MU_MEHROTRA; CMPC_MU_MONOTONE = IPOPT's default */
-                                            /* Fiacco-McCormick update (iterate-for-iterate the reference's solver path); */
+                                            /* Fiacco-McCormick update with IPOPT's constants, NLP scaling, termination   */
+                                            /* and acceptable-level tests; NOT restated: restoration phase, second-order  */
+                                            /* correction, watchdog (a solve IPOPT would rescue through them ends with    */
+                                            /* CMPC_STATUS_LINE_SEARCH here);                                             */
                                             /* CMPC_MU_MEHROTRA = predictor-corrector (mu from the affine-scaling step,   */
                                             /* second-order corrector on the same factorisation, ~0.63 x the iterations;  */
                                             /* same termination test; an instance it cannot finish is re-solved monotone) */
@@ -85,6 +92,13 @@ typedef struct cmpc_config {
                                             /* 0 = default 0.01 (closed loop at tol 1e-4: 4.4 instead of 5.4 iterations per   */
                                             /* tick with IPOPT's cold-start value 0.1; smaller values lengthen the slowest    */
                                             /* solves of a batch)                                                            */
+    double nlp_scaling_max_gradient;        /* IPOPT nlp_scaling_max_gradient (gradient-based scaling, IPOPT's default method): the  */
+                                            /* solve runs on  min(1, max_gradient / |grad f(x0)|_inf) * f ; ipopt_tolerance applies */
+                                            /* to that scaled problem (dual_inf_tol 1, constr_viol_tol / compl_inf_tol 1e-4 to the   */
+                                            /* unscaled one).  0 = IPOPT's default 100, negative = no scaling.  Rows of g are never  */
+                                            /* scaled: their gradients are bounded far below 100              */
+    double acceptable_tol;                  /* IPOPT acceptable_tol: 0 = IPOPT's default 1e-6, negative = off                        */
+    int acceptable_iter;                    /* IPOPT acceptable_iter: 0 = IPOPT's default 15                                         */
 } cmpc_config;
 #define CMPC_MU_DEFAULT 0
 #define CMPC_MU_MONOTONE 1

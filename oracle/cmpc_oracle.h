@@ -77,12 +77,22 @@ typedef struct cmpc_oracle_ipm_opts {
                               * 1: Mehrotra predictor-corrector barrier update (mu from the affine-scaling step, second-order
                               *    corrector with the same factorisation), the mu strategy of the CUDA path's default mode;
                               *    instances it cannot finish are re-solved on the monotone path                       */
+    double nlp_scaling_max_gradient; /* IPOPT nlp_scaling_method gradient-based (its default): f is scaled by
+                              * min(1, max_gradient / |grad f(x0)|_inf), row i of g by min(1, max_gradient / |grad g_i(x0)|_inf),
+                              * floor nlp_scaling_min_value 1e-8; tol applies to the SCALED problem, dual_inf_tol /
+                              * constr_viol_tol / compl_inf_tol to the unscaled one.  Default 100; 0 = no scaling           */
+    double acceptable_tol;   /* IPOPT acceptable_tol 1e-6 (with acceptable_dual_inf_tol 1e10, acceptable_constr_viol_tol 1e-2,
+                              * acceptable_compl_inf_tol 1e-2): acceptable_iter consecutive acceptable iterates end the solve
+                              * with status 5 ("Solved To Acceptable Level"); a line-search / numerical failure at an
+                              * acceptable point also reports 5.  0 = off                                                  */
+    int acceptable_iter;     /* IPOPT acceptable_iter 15                                                                   */
 } cmpc_oracle_ipm_opts;
 
 void cmpc_oracle_ipm_default_opts(cmpc_oracle_ipm_opts* o);
 
 typedef struct cmpc_oracle_ipm_stats {
-    int status;      /* 0 converged, 1 max_iter, 2 line-search failure, 3 numerical failure, 4 bad input */
+    int status;      /* 0 converged, 1 max_iter, 2 line-search failure, 3 numerical failure, 4 bad input,
+                      * 5 solved to acceptable level                                                       */
     int iters;
     double obj;
     double kkt_error;   /* final scaled optimality error E_0                */
@@ -90,6 +100,8 @@ typedef struct cmpc_oracle_ipm_stats {
     int n_reg;          /* iterations that needed delta_w > 0                */
     int n_ls_trials;    /* total backtracking trials                         */
     int n_fallback;     /* 1: the predictor-corrector run failed, monotone re-solve */
+    double obj_scaling;     /* d_f of the gradient-based scaling (1 = none)              */
+    double min_g_scaling;   /* smallest row scaling d_c (1 = no row was scaled)          */
 } cmpc_oracle_ipm_stats;
 
 /* callbacks so that the same IPM can run on the restated NLP or on the compiled reference functions */

@@ -21,8 +21,12 @@
  *   * kappa_sigma 1e10 safeguard of the bound multipliers                                                     (eq. 16)
  *   * kappa_d 1e-5 damping of one-sided slacks                                                                 (sec. 3.7)
  *   * termination on the scaled optimality error E_0 <= tol with s_max 100                                    (eq. 5, 6)
- * NOT restated: restoration phase, second-order correction, watchdog, NLP gradient scaling, acceptable-point
- * termination (documented in DESIGN.md).  The linear algebra is deliberately generic (banded LU with partial pivoting of
+ *   * nlp_scaling_method gradient-based with nlp_scaling_max_gradient 100 (IPOPT's default): objective and constraint rows
+ *     scaled from the derivatives at the initial point; tol applies to the scaled problem, dual_inf_tol 1 /
+ *     constr_viol_tol 1e-4 / compl_inf_tol 1e-4 to the unscaled one (IpIpoptCalculatedQuantities / OptimalityErrorConvergenceCheck)
+ *   * acceptable-point termination: acceptable_tol 1e-6 for acceptable_iter 15 consecutive iterations, or an acceptable
+ *     current point when the line search / the regularisation gives up ("Solved To Acceptable Level", status 5)
+ * NOT restated: restoration phase, second-order correction, watchdog (documented in DESIGN.md).  The linear algebra is deliberately generic (banded LU with partial pivoting of
  * the stage-ordered condensed KKT matrix) so that it is independent of the Riccati recursion of the CUDA path.
  *
  * SOLVER-LEVEL PARITY UNPINNED (no IPOPT/CasADi in this container, no reference goldens); see cmpc_oracle.h.
@@ -49,6 +53,9 @@ void cmpc_oracle_ipm_default_opts(cmpc_oracle_ipm_opts* o)
     o->warm_duals = 0;
     o->verbose = 0;
     o->mehrotra = 0;
+    o->nlp_scaling_max_gradient = 100.0;
+    o->acceptable_tol = 1e-6;
+    o->acceptable_iter = 15;
 }
 
 /* IPOPT constants (defaults of 3.13/3.14) */
@@ -204,6 +211,8 @@ typedef struct ipm_ws {
     double *xt, *st, *gt;                   /* trial */
     double *rhs, *sigma, *rs, *rd;
     double *muL, *muU;                      /* complementarity target of every bound (mu, or mu -+ the Mehrotra corrector) */
+    /* gradient-based NLP scaling (IPOPT nlp_scaling_method): f_s = df f, g_s = Dc g */
+    double df; double* dcs; double* ytmp;
     /* KKT ordering */
     int nK; int* perm; /* unknown u (0..nK-1: x then eq slots) -> position */
     band K;
@@ -229,11 +238,35 @@ static void lag_grad(const ipm_ws* W, const double* y, double* out)
     }
 }
 
-typedef struct errs { double dual, viol, compl_, E; } errs;
+typedef struct errs { double dual, viol, compl_, E; double dual_u, viol_u, compl_u; /* unscaled */ } errs;
+
+/* the NLP functions of the SCALED problem */
+static void s_jac_fg(const ipm_ws* W, const double* x, const double* p, double* f, double* grad, double* g, double* jnz)
+{
+    const cmpc_oracle_nlp_fn* F = W->nlp;
+    F->jac_fg(F->ctx, x, p, f, grad, g, jnz);
+    *f *= W->df;
+    for (int c = 0; c < W->n; ++c) grad[c] *= W->df;
+    for (int r = 0; r < W->m; ++r) g[r] *= W->dcs[r];
+    for (int q = 0; q < F->nnz_j; ++q) jnz[q] *= W->dcs[F->jr[q]];
+}
+static void s_fg(const ipm_ws* W, const double* x, const double* p, double* f, double* g)
+{
+    const cmpc_oracle_nlp_fn* F = W->nlp;
+    F->fg(F->ctx, x, p, f, g);
+    *f *= W->df;
+    for (int r = 0; r < W->m; ++r) g[r] *= W->dcs[r];
+}
+static void s_hess(const ipm_ws* W, const double* x, const double* p, const double* y, double* hnz)
+{
+    const cmpc_oracle_nlp_fn* F = W->nlp;
+    for (int r = 0; r < W->m; ++r) W->ytmp[r] = W->dcs[r] * y[r];
+    F->hess(F->ctx, x, p, W->df, W->ytmp, hnz);
+}
 
 static errs kkt_error(const ipm_ws* W, double mu, double* scratch)
 {
-    errs e = {0, 0, 0, 0};
+    errs e = {0, 0, 0, 0, 0, 0, 0};
     lag_grad(W, W->y, scratch);
     e.dual = vmaxabs(scratch, W->n);
     double sumy = 0, sumz = 0; int nb = 0;
@@ -243,10 +276,12 @@ static errs kkt_error(const ipm_ws* W, double mu, double* scratch)
         if (W->rtype[r] == 0) {
             double c = W->g[r] - W->target[W->rslot[r]];
             if (fabs(c) > e.viol) e.viol = fabs(c);
+            if (fabs(c) / W->dcs[r] > e.viol_u) e.viol_u = fabs(c) / W->dcs[r];
         } else {
             int i = W->rslot[r];
             double d = W->g[r] - W->s[i];
             if (fabs(d) > e.viol) e.viol = fabs(d);
+            if (fabs(d) / W->dcs[r] > e.viol_u) e.viol_u = fabs(d) / W->dcs[r];
             double ds_ = -W->y[r];
             if (W->hasL[i]) { ds_ -= W->zL[i]; sumz += W->zL[i]; nb++; double c = (W->s[i] - W->sL[i]) * W->zL[i] - mu; if (fabs(c) > e.compl_) e.compl_ = fabs(c); }
             if (W->hasU[i]) { ds_ += W->zU[i]; sumz += W->zU[i]; nb++; double c = (W->sU[i] - W->s[i]) * W->zU[i] - mu; if (fabs(c) > e.compl_) e.compl_ = fabs(c); }
@@ -257,6 +292,7 @@ static errs kkt_error(const ipm_ws* W, double mu, double* scratch)
     double sd = fmax(S_MAX, (sumy + sumz) / fmax(1, mact + nb)) / S_MAX;
     double sc = fmax(S_MAX, sumz / fmax(1, nb)) / S_MAX;
     e.E = fmax(e.dual / sd, fmax(e.viol, e.compl_ / sc));
+    e.dual_u = e.dual / W->df; e.compl_u = e.compl_ / W->df;
     return e;
 }
 
@@ -389,6 +425,7 @@ static void ws_free(ipm_ws* W)
     free(W->dx); free(W->ds); free(W->dy); free(W->dzL); free(W->dzU);
     free(W->grad); free(W->g); free(W->jnz); free(W->hnz); free(W->xt); free(W->st); free(W->gt);
     free(W->rhs); free(W->sigma); free(W->rs); free(W->rd); free(W->perm); free(W->muL); free(W->muU);
+    free(W->dcs); free(W->ytmp);
     band_free(&W->K);
 }
 
@@ -416,7 +453,34 @@ static int ipm_core(const cmpc_oracle_nlp_fn* F, int N, const cmpc_oracle_ipm_op
             }
         free(fill);
     }
-    /* classify rows */
+    /* gradient-based scaling from the derivatives at the initial point (IPOPT GradientScaling::DetermineScalingParametersImpl) */
+    W->df = 1.0; W->dcs = ALLOCD(m); W->ytmp = ALLOCD(m);
+    W->x = ALLOCD(n); W->grad = ALLOCD(n); W->g = ALLOCD(m); W->jnz = ALLOCD(F->nnz_j);
+    for (int r = 0; r < m; ++r) W->dcs[r] = 1.0;
+    memcpy(W->x, x, sizeof(double) * n);
+    stats->obj_scaling = stats->min_g_scaling = 1.0;
+    if (opts->nlp_scaling_max_gradient > 0.0) {
+        const double gmax = opts->nlp_scaling_max_gradient, smin = 1e-8;
+        double f0;
+        F->jac_fg(F->ctx, W->x, p, &f0, W->grad, W->g, W->jnz);
+        double a = vmaxabs(W->grad, n);
+        if (a > gmax) W->df = fmax(gmax / a, smin);
+        double* rmax = ALLOCD(m);
+        for (int q = 0; q < F->nnz_j; ++q) if (fabs(W->jnz[q]) > rmax[F->jr[q]]) rmax[F->jr[q]] = fabs(W->jnz[q]);
+        for (int r = 0; r < m; ++r) {
+            if (rmax[r] > gmax) W->dcs[r] = fmax(gmax / rmax[r], smin);
+            if (W->dcs[r] < stats->min_g_scaling) stats->min_g_scaling = W->dcs[r];
+        }
+        free(rmax);
+        stats->obj_scaling = W->df;
+    }
+    double* lbs = ALLOCD(m); double* ubs = ALLOCD(m);
+    for (int r = 0; r < m; ++r) {
+        lbs[r] = lbg[r] > -opts->inf_bound ? lbg[r] * W->dcs[r] : lbg[r];
+        ubs[r] = ubg[r] < opts->inf_bound ? ubg[r] * W->dcs[r] : ubg[r];
+    }
+    /* classify rows (from here on lbg / ubg are the bounds of the scaled rows) */
+    lbg = lbs; ubg = ubs;
     W->rtype = ALLOCI(m); W->rslot = ALLOCI(m);
     int mE = 0, mI = 0, bad = 0;
     for (int r = 0; r < m; ++r) {
@@ -439,9 +503,9 @@ static int ipm_core(const cmpc_oracle_nlp_fn* F, int N, const cmpc_oracle_ipm_op
             W->sU[i] = W->hasU[i] ? ubg[r] + opts->bound_relax * fmax(1.0, fabs(ubg[r])) : INFINITY;
         }
     }
-    W->x = ALLOCD(n); W->s = ALLOCD(mI); W->y = ALLOCD(m); W->zL = ALLOCD(mI); W->zU = ALLOCD(mI);
+    W->s = ALLOCD(mI); W->y = ALLOCD(m); W->zL = ALLOCD(mI); W->zU = ALLOCD(mI);
     W->dx = ALLOCD(n); W->ds = ALLOCD(mI); W->dy = ALLOCD(m); W->dzL = ALLOCD(mI); W->dzU = ALLOCD(mI);
-    W->grad = ALLOCD(n); W->g = ALLOCD(m); W->jnz = ALLOCD(F->nnz_j); W->hnz = ALLOCD(F->nnz_h);
+    W->hnz = ALLOCD(F->nnz_h);
     W->xt = ALLOCD(n); W->st = ALLOCD(mI); W->gt = ALLOCD(m);
     W->nK = n + mE;
     W->muL = ALLOCD(mI); W->muU = ALLOCD(mI);
@@ -468,12 +532,11 @@ static int ipm_core(const cmpc_oracle_nlp_fn* F, int N, const cmpc_oracle_ipm_op
         }
         band_alloc(&W->K, W->nK, bw, bw);
     }
-    if (bad) { stats->status = 4; ws_free(W); return 4; }
+    if (bad) { stats->status = 4; ws_free(W); free(lbs); free(ubs); return 4; }
 
     /* ---------------- initial point */
-    memcpy(W->x, x, sizeof(double) * n);
     double f;
-    F->jac_fg(F->ctx, W->x, p, &f, W->grad, W->g, W->jnz);
+    s_jac_fg(W, W->x, p, &f, W->grad, W->g, W->jnz);
     for (int i = 0; i < mI; ++i) {
         double s = W->g[W->irow[i]];
         double k1 = opts->bound_push, k2 = opts->bound_push;
@@ -488,7 +551,7 @@ static int ipm_core(const cmpc_oracle_nlp_fn* F, int N, const cmpc_oracle_ipm_op
         W->zU[i] = W->hasU[i] ? 1.0 : 0.0;
     }
     if (opts->warm_duals && lam_g) {
-        for (int r = 0; r < m; ++r) W->y[r] = W->rtype[r] == 2 ? 0.0 : lam_g[r];
+        for (int r = 0; r < m; ++r) W->y[r] = W->rtype[r] == 2 ? 0.0 : lam_g[r] * W->df / W->dcs[r];   /* lam_g: unscaled problem */
         for (int i = 0; i < mI; ++i) {
             double yv = W->y[W->irow[i]];
             if (W->hasL[i]) W->zL[i] = fmax(yv < 0 ? -yv : 0.0, opts->mu_init / (W->s[i] - W->sL[i]));
@@ -496,22 +559,27 @@ static int ipm_core(const cmpc_oracle_nlp_fn* F, int N, const cmpc_oracle_ipm_op
         }
     }
     double mu = opts->mu_init, tau = fmax(TAU_MIN, 1.0 - mu);
-    /* IPOPT: the barrier parameter stops at min(tol, compl_inf_tol) / (barrier_tol_factor + 1), compl_inf_tol = 1e-4 */
-    const double mu_min = fmin(opts->tol, 1e-4) / (KAPPA_EPS + 1.0);
+    /* IPOPT: the barrier parameter stops at min(tol, compl_inf_tol) / (barrier_tol_factor + 1), compl_inf_tol = 1e-4 "posed to
+     * the scaled problem" (MonotoneMuUpdate::CalcNewMuAndTau: apply_obj_scaling(compl_inf_tol)) */
+    const double mu_min = fmin(opts->tol, 1e-4 * W->df) / (KAPPA_EPS + 1.0);
     double theta0 = infeas_l1(W, W->g, W->s);
     const double theta_max = 1e4 * fmax(1.0, theta0), theta_min = 1e-4 * fmax(1.0, theta0);
     double filt_t[MAX_FILTER], filt_p[MAX_FILTER]; int nfilt = 0;
     double dw_last = 0.0;
     int status = 1, it = 0;
-    errs e0 = {0, 0, 0, 0};
+    errs e0 = {0, 0, 0, 0, 0, 0, 0};
     double* scratch = ALLOCD(n);
+    int nacc = 0;   /* consecutive acceptable iterates */
 
     for (it = 0; it <= opts->max_iter; ++it) {
         e0 = kkt_error(W, 0.0, scratch);
         if (opts->verbose)
             fprintf(stderr, "it %3d f %.10e  E0 %.2e (d %.2e v %.2e c %.2e) mu %.1e dw %.1e\n", it, f, e0.E, e0.dual,
                     e0.viol, e0.compl_, mu, dw_last);
-        if (e0.E <= opts->tol && e0.dual <= 1.0 && e0.viol <= 1e-4 && e0.compl_ <= 1e-4) { status = 0; break; }
+        if (e0.E <= opts->tol && e0.dual_u <= 1.0 && e0.viol_u <= 1e-4 && e0.compl_u <= 1e-4) { status = 0; break; }
+        if (opts->acceptable_tol > 0.0 && e0.E <= opts->acceptable_tol && e0.dual_u <= 1e10 && e0.viol_u <= 1e-2 && e0.compl_u <= 1e-2) {
+            if (++nacc >= opts->acceptable_iter) { status = 5; break; }
+        } else nacc = 0;
         if (it == opts->max_iter || (mehrotra && it == PC_MAX_ITER)) { status = 1; break; }
         /* barrier parameter update (eq. 7); in predictor-corrector mode mu follows from the affine step below */
         while (!mehrotra) {
@@ -523,7 +591,7 @@ static int ipm_core(const cmpc_oracle_nlp_fn* F, int N, const cmpc_oracle_ipm_op
             } else break;
         }
         /* search direction with inertia correction (alg. IC) */
-        F->hess(F->ctx, W->x, p, 1.0, W->y, W->hnz);
+        s_hess(W, W->x, p, W->y, W->hnz);
         double dc = DC_BAR * pow(mu, KAPPA_C);
         double dw = 0.0; int rc, tries = 0;
         for (int i = 0; i < mI; ++i) W->muL[i] = W->muU[i] = mehrotra ? 0.0 : mu;   /* predictor: affine-scaling step */
@@ -603,7 +671,7 @@ static int ipm_core(const cmpc_oracle_nlp_fn* F, int N, const cmpc_oracle_ipm_op
             stats->n_ls_trials++;
             for (int c = 0; c < n; ++c) W->xt[c] = W->x[c] + alpha * W->dx[c];
             for (int i = 0; i < mI; ++i) W->st[i] = W->s[i] + alpha * W->ds[i];
-            F->fg(F->ctx, W->xt, p, &ft, W->gt);
+            s_fg(W, W->xt, p, &ft, W->gt);
             double th_t = infeas_l1(W, W->gt, W->st);
             double ph_t = barrier_obj(W, ft, W->st, mu);
             int ok = isfinite(ph_t) && isfinite(th_t) && th_t <= theta_max;
@@ -649,16 +717,20 @@ static int ipm_core(const cmpc_oracle_nlp_fn* F, int N, const cmpc_oracle_ipm_op
             }
         }
         for (int r = 0; r < m; ++r) W->y[r] += alpha * W->dy[r];
-        F->jac_fg(F->ctx, W->x, p, &f, W->grad, W->g, W->jnz);
+        s_jac_fg(W, W->x, p, &f, W->grad, W->g, W->jnz);
     }
+    /* IPOPT: when the algorithm cannot continue at a point that passes the acceptable-level test it stops there
+     * (STOP_AT_ACCEPTABLE_POINT) instead of reporting the failure */
+    if ((status == 2 || status == 3) && nacc > 0) status = 5;
     free(scratch);
     memcpy(x, W->x, sizeof(double) * n);
-    if (lam_g) memcpy(lam_g, W->y, sizeof(double) * m);
+    if (lam_g) for (int r = 0; r < m; ++r) lam_g[r] = W->y[r] * W->dcs[r] / W->df;   /* multipliers of the unscaled problem */
     stats->status = status;
     stats->iters = it;
-    stats->obj = f;
-    stats->kkt_error = e0.E; stats->dual_inf = e0.dual; stats->constr_viol = e0.viol; stats->compl_inf = e0.compl_;
+    stats->obj = f / W->df;
+    stats->kkt_error = e0.E; stats->dual_inf = e0.dual_u; stats->constr_viol = e0.viol_u; stats->compl_inf = e0.compl_u;
     ws_free(W);
+    free(lbs); free(ubs);
     return status;
 }
 

@@ -37,13 +37,15 @@ class Cfg(C.Structure):
 class IpmOpts(C.Structure):
     _fields_ = [("tol", C.c_double), ("max_iter", C.c_int), ("mu_init", C.c_double), ("bound_relax", C.c_double),
                 ("bound_push", C.c_double), ("inf_bound", C.c_double), ("warm_duals", C.c_int),
-                ("verbose", C.c_int), ("mehrotra", C.c_int)]
+                ("verbose", C.c_int), ("mehrotra", C.c_int), ("nlp_scaling_max_gradient", C.c_double),
+                ("acceptable_tol", C.c_double), ("acceptable_iter", C.c_int)]
 
 
 class IpmStats(C.Structure):
     _fields_ = [("status", C.c_int), ("iters", C.c_int), ("obj", C.c_double), ("kkt_error", C.c_double),
                 ("dual_inf", C.c_double), ("constr_viol", C.c_double), ("compl_inf", C.c_double),
-                ("n_reg", C.c_int), ("n_ls_trials", C.c_int), ("n_fallback", C.c_int)]
+                ("n_reg", C.c_int), ("n_ls_trials", C.c_int), ("n_fallback", C.c_int), ("obj_scaling", C.c_double),
+                ("min_g_scaling", C.c_double)]
 
 
 def make_cfg(N=12, dT=0.1, mu=0.33, w_com=(10.0, 10.0, 200.0), w_h=100.0, w_pos=200.0, w_sym=10.0,

@@ -16,7 +16,7 @@ from .layout import Layout  # noqa: F401
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CMPC_B200_LIB", os.path.join(HERE, "libcmpc_b200.so"))  # override: A/B builds under profiles/_build
 
-STATUS_NAMES = {0: "converged", 1: "max_iter", 2: "line_search", 3: "numerical", 4: "bad_input"}
+STATUS_NAMES = {0: "converged", 1: "max_iter", 2: "line_search", 3: "numerical", 4: "bad_input", 5: "acceptable"}
 
 
 class CmpcConfig(C.Structure):
@@ -29,7 +29,8 @@ class CmpcConfig(C.Structure):
                 ("mu_init", C.c_double), ("bound_relax_factor", C.c_double), ("bound_push", C.c_double),
                 ("infinity", C.c_double), ("device", C.c_int), ("threads_per_instance", C.c_int),
                 ("ctas_per_sm", C.c_int), ("teams_per_cta", C.c_int), ("lockstep_groups", C.c_int),
-                ("mu_strategy", C.c_int), ("warm_start_mu_init", C.c_double)]
+                ("mu_strategy", C.c_int), ("warm_start_mu_init", C.c_double), ("nlp_scaling_max_gradient", C.c_double),
+                ("acceptable_tol", C.c_double), ("acceptable_iter", C.c_int)]
 
 
 _dp = C.POINTER(C.c_double)

@@ -48,6 +48,9 @@ struct Config {
     int pc;              // 1: Mehrotra predictor-corrector barrier update, 0: IPOPT's monotone update (mu_strategy)
     double mu_warm;      // barrier parameter of a solve that starts from given multipliers (warm_duals): floor of the bound
                          // multipliers mu_warm / slack and first mu of the monotone update
+    double scal_max_grad;  // nlp_scaling_max_gradient (IPOPT default 100; 0: no scaling of the objective)
+    double acc_tol;        // acceptable_tol (IPOPT default 1e-6; 0: no acceptable-level termination)
+    int acc_iter;          // acceptable_iter (IPOPT default 15)
 };
 
 struct Instance {  // CasADi order, read only

@@ -748,7 +748,6 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
     CMPC_LANES_END
     double* filt_t = ism.filt_t;
     double* filt_p = ism.filt_p;
-    const double mu_min = fmin(cfg.tol, 1e-4) / (KAPPA_EPS + 1.0);  // IPOPT: min(tol, compl_inf_tol) / (barrier_tol_factor + 1)
     const double refine_tol = fmin(REFINE_TOL, 0.1 * cfg.tol);  // residual of the linear system that triggers a refinement sweep
 
     // state of the instance the team is working on (thread-private copies, uniform over the team)
@@ -760,6 +759,15 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
     bool warm = false;
     double mu = cfg.mu_init, tau = TAU_MIN, f = 0, theta0 = 0, bar0 = 0, theta_max = 0, theta_min = 0, dw_last = 0, E0 = 0;
     int nfilt = 0, it = 0, it_base = 0;
+    // IPOPT's gradient-based NLP scaling (nlp_scaling_method, its default): the solver works on  sf * f  with
+    // sf = min(1, nlp_scaling_max_gradient / |grad f(x0)|_inf).  Instead of scaling the weights in every hot loop the driver
+    // runs the UNSCALED problem with the equivalent parameters: for the scaled problem's (mu, z, lambda, phi, delta_w,
+    // delta_c) the unscaled run uses (mu / sf, z / sf, lambda / sf, phi / sf, delta_w / sf, delta_c * sf) -- the Newton
+    // system, the step lengths and the iterates are identical -- and every test IPOPT poses to the scaled problem (E_mu,
+    // filter, switching condition, mu update) is evaluated on the re-scaled statistics.  Rows of g are never scaled: every
+    // entry of the constraint jacobian is bounded by 1, dT, dT |rho| or dT |F| (far below 100 for any physical input).
+    double sf = 1.0, isf = 1.0, mu_min = fmin(cfg.tol, 1e-4) / (KAPPA_EPS + 1.0);
+    int nacc = 0;            // consecutive iterates that pass IPOPT's acceptable-level test
     bool pc = cfg.pc != 0;   // Mehrotra predictor-corrector barrier update (false: IPOPT's monotone update)
     bool redo = false;       // the predictor-corrector run of the instance failed: solve it again on the monotone path
     bool first = true;       // the next instance of the team is its static one
@@ -877,9 +885,29 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
             cta.template maxv<1>(bad);
             team_sync<NT, G>(T);
             if (fresh && bad[0] != 0.0) { fin = 4; fresh = false; f = 0; it = 0; E0 = 0; }
-            // initial point: slacks pushed inside their bounds (bound_push / bound_frac), bound multipliers 1
             T.on = fresh;
-            if (fresh) { mu = warm ? cfg.mu_warm : cfg.mu_init; tau = fmax(TAU_MIN, 1.0 - mu); nfilt = 0; dw_last = 0.0; it = 0; }
+            // objective scaling from the gradient at the initial point (IPOPT GradientScaling, nlp_scaling_min_value 1e-8)
+            {
+                double gmax[1] = {0.0};
+                if (cfg.scal_max_grad > 0.0) {
+    CMPC_LANES
+        CMPC_ROLES(NS + NU) CMPC_KNOTS(0, N) {
+            if (k == N && r >= NS) continue;
+            gmax[0] = fmax(gmax[0], fabs(grad_entry(cfg, w, w.z, k, r)));
+        }
+    CMPC_LANES_END_NOSYNC
+                    cta.template maxv<1>(gmax);
+                    team_sync<NT, G>(T);
+                }
+                if (fresh) {
+                    sf = (cfg.scal_max_grad > 0.0 && gmax[0] > cfg.scal_max_grad) ? fmax(cfg.scal_max_grad / gmax[0], 1e-8) : 1.0;
+                    isf = 1.0 / sf;
+                    // IPOPT: mu stops at min(tol, compl_inf_tol posed to the scaled problem) / (barrier_tol_factor + 1)
+                    mu_min = fmin(cfg.tol, 1e-4 * sf) / (KAPPA_EPS + 1.0);
+                }
+            }
+            // initial point: slacks pushed inside their bounds (bound_push / bound_frac), bound multipliers 1
+            if (fresh) { mu = warm ? cfg.mu_warm : cfg.mu_init; tau = fmax(TAU_MIN, 1.0 - mu); nfilt = 0; dw_last = 0.0; it = 0; nacc = 0; }
             eval_point<NT, G>(T, cta, cfg, ism, w.z, w.sl);  // path row values (the slacks are not set yet)
     CMPC_LANES
         for (int it = lane; it < N * 64; it += NT) {
@@ -898,11 +926,11 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
             } else if (hl) s = fmax(s, sl + k1 * fmax(1.0, fabs(sl)));
             else s = fmin(s, su - k1 * fmax(1.0, fabs(su)));
             w.sl[pr] = s;
-            double zl = hl ? 1.0 : 0.0, zu = hu ? 1.0 : 0.0;
+            double zl = hl ? isf : 0.0, zu = hu ? isf : 0.0;   // bound_mult_init_val 1 of the scaled problem
             if (warm) {
                 const double yv = w.yp[pr];
-                if (hl) zl = fmax(yv < 0 ? -yv : 0.0, cfg.mu_warm / (s - sl));
-                if (hu) zu = fmax(yv > 0 ? yv : 0.0, cfg.mu_warm / (su - s));
+                if (hl) zl = fmax(yv < 0 ? -yv : 0.0, cfg.mu_warm * isf / (s - sl));
+                if (hu) zu = fmax(yv > 0 ? yv : 0.0, cfg.mu_warm * isf / (su - s));
             }
             w.zl[pr] = zl; w.zu[pr] = zu;
         }
@@ -921,11 +949,20 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
         kkt_pass<NT, G>(T, cta, cfg, ism);
         CMPC_TOC(1)
         KktStats ks = ism.ks;
+        const double dual_u = ks.dual;   // dual infeasibility of the unscaled problem (dual_inf_tol applies to it)
+        ks.dual *= sf; ks.pmax *= sf; ks.pmin *= sf; ks.sum_y *= sf; ks.sum_z *= sf;   // statistics of the scaled problem
         if (act) {
             double cmp0;
             E0 = kkt_E(ks, 0.0, &cmp0);
-            if (E0 <= cfg.tol && ks.dual <= 1.0 && ks.viol <= 1e-4 && cmp0 <= 1e-4) { fin = 0; act = false; }
-            else if (it == cfg.max_iter || (pc && it == PC_MAX_ITER)) { fin = 1; act = false; }
+            const double cmp_u = cmp0 * isf;
+            if (E0 <= cfg.tol && dual_u <= 1.0 && ks.viol <= 1e-4 && cmp_u <= 1e-4) { fin = 0; act = false; }
+            else {
+                // acceptable_tol / acceptable_dual_inf_tol 1e10 / acceptable_constr_viol_tol 1e-2 / acceptable_compl_inf_tol 1e-2
+                if (cfg.acc_tol > 0.0 && E0 <= cfg.acc_tol && dual_u <= 1e10 && ks.viol <= 1e-2 && cmp_u <= 1e-2) ++nacc;
+                else nacc = 0;
+                if (cfg.acc_tol > 0.0 && nacc >= cfg.acc_iter) { fin = 5; act = false; }
+                else if (it == cfg.max_iter || (pc && it == PC_MAX_ITER)) { fin = 1; act = false; }
+            }
         }
         if (act && !pc) {
             // barrier update (eq. 7), filter reset
@@ -936,26 +973,26 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
             }
         }
         // ---- search direction with inertia correction (alg. IC): Cholesky failure inside the Riccati sweep <=> wrong inertia
-        const double dc = fmax(DC_BAR * sqrt(sqrt(mu)), DC_FLOOR);
-        double dw = 0.0;
+        const double dc = fmax(DC_BAR * sqrt(sqrt(mu)), DC_FLOOR) * sf;   // delta_c of the scaled problem, times sf
+        double dw = 0.0;                                                  // delta_w of the scaled problem, divided by sf
         int tries = 0;
         bool needf = act;
         while (vote_any<G>(T, needf)) {
             T.on = needf;
-            barrier_pass<NT, G>(T, cfg, w, pc ? 0.0 : mu, dw, dc);  // predictor-corrector: affine-scaling step first
+            barrier_pass<NT, G>(T, cfg, w, pc ? 0.0 : mu * isf, dw, dc);  // predictor-corrector: affine-scaling step first
             CMPC_TOC(2)
             const int rc = riccati_backward<NT, G>(T, cfg, io, sm, dw);
             CMPC_TOC(3)
             if (needf) {
                 if (rc == 0) needf = false;
                 else {
-                    if (dw == 0.0) dw = dw_last == 0.0 ? DW_FIRST : fmax(DW_MIN, KW_MINUS * dw_last);
+                    if (dw == 0.0) dw = (dw_last == 0.0 ? DW_FIRST : fmax(DW_MIN, KW_MINUS * dw_last)) * isf;
                     else dw *= (dw_last == 0.0 ? KW_PLUS_FIRST : KW_PLUS);
-                    if (dw > DW_MAX || ++tries > 60) { needf = false; fin = 3; act = false; }
+                    if (dw * sf > DW_MAX || ++tries > 60) { needf = false; fin = 3; act = false; }
                 }
             }
         }
-        if (act && dw > 0.0) dw_last = dw;
+        if (act && dw > 0.0) dw_last = dw * sf;
         T.on = act;
         riccati_forward<NT, G>(T, cfg, io, sm, false);
         CMPC_TOC(4)
@@ -965,8 +1002,9 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
             const bool pcact = act && pc;
             if (vote_any<G>(T, pcact)) {
                 T.on = pcact;
-                affine_pass<NT, G>(T, cta, cfg, ism, mu_min, mu);
-                if (pcact) { tau = fmax(TAU_MIN, 1.0 - mu); nfilt = 0; }
+                double mu_u = mu * isf;
+                affine_pass<NT, G>(T, cta, cfg, ism, mu_min * isf, mu_u);
+                if (pcact) { mu = mu_u * sf; tau = fmax(TAU_MIN, 1.0 - mu); nfilt = 0; }
                 CMPC_TOC(5)
                 refine_backward<NT, G>(T, cfg, io, sm);
                 CMPC_TOC(15)
@@ -975,30 +1013,30 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
                 T.on = act;
             }
         }
-        recover_pass<NT, G>(T, cfg, w, mu, dw, dc, pc);
+        recover_pass<NT, G>(T, cfg, w, mu * isf, dw, dc, pc);
         CMPC_TOC(5)
-        step_pass<NT, G>(T, cta, cfg, ism, mu, dw, tau);
+        step_pass<NT, G>(T, cta, cfg, ism, mu * isf, dw, tau);
         StepStats ss = ism.ss;
         CMPC_TOC(6)
         // ---- iterative refinement on the stationarity residual of the Newton system (the eliminated rows hold exactly)
         double rho_prev = HUGE_VAL;
         int rf = 0;
         for (;;) {
-            const bool needr = act && rf < MAX_REFINE && ss.rho > refine_tol && !(ss.rho > 0.5 * rho_prev);
+            const bool needr = act && rf < MAX_REFINE && ss.rho * sf > refine_tol && !(ss.rho > 0.5 * rho_prev);
             if (!vote_any<G>(T, needr)) break;
             T.on = needr;
             if (needr) rho_prev = ss.rho;
             refine_backward<NT, G>(T, cfg, io, sm);
             riccati_forward<NT, G>(T, cfg, io, sm, true);
-            recover_pass<NT, G>(T, cfg, w, mu, dw, dc, pc);
-            step_pass<NT, G>(T, cta, cfg, ism, mu, dw, tau);
+            recover_pass<NT, G>(T, cfg, w, mu * isf, dw, dc, pc);
+            step_pass<NT, G>(T, cta, cfg, ism, mu * isf, dw, tau);
             if (needr) { ss = ism.ss; ++rf; }
         }
         CMPC_TOC(7)
         if (act && ss.bad != 0.0) { fin = 3; act = false; }
-        const double amax = ss.amax, az = ss.az, dphi = ss.dphi;
-        // ---- filter line search (alg. A)
-        const double theta = theta0, phi = f + mu * bar0;  // barrier function of the current point for the current mu
+        const double amax = ss.amax, az = ss.az, dphi = ss.dphi * sf;
+        // ---- filter line search (alg. A) on the scaled problem: phi = sf f + mu (barrier sum)
+        const double theta = theta0, phi = sf * f + mu * bar0;  // barrier function of the current point for the current mu
         double amin;
         if (dphi < 0) {
             amin = fmin(GAMMA_THETA, GAMMA_PHI * theta / (-dphi));
@@ -1022,7 +1060,7 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
             CMPC_LANES_END
             eval_point<NT, G>(T, cta, cfg, ism, w.zt, w.slt);
             if (pend) {
-                ft = ism.es.f; th_t = ism.es.theta; bar_t = ism.es.bar; ph_t = ft + mu * bar_t;
+                ft = ism.es.f; th_t = ism.es.theta; bar_t = ism.es.bar; ph_t = sf * ft + mu * bar_t;
                 bool ok = (fabs(ph_t) < HUGE_VAL) && (fabs(th_t) < HUGE_VAL) && th_t <= theta_max;
                 for (int q = 0; ok && q < nfilt; ++q)
                     if (th_t >= filt_t[q] && ph_t >= filt_p[q]) ok = false;
@@ -1062,6 +1100,7 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
                 double* __restrict__ yp = w.yp; double* __restrict__ zlp = w.zl; double* __restrict__ zup = w.zu;
                 const double* __restrict__ lo = w.lo; const double* __restrict__ up = w.up; const double* __restrict__ slp = w.sl;
                 const double* __restrict__ dyp = w.dyp; const double* __restrict__ dzl = w.dzl; const double* __restrict__ dzu = w.dzu;
+                const double mu_u = mu * isf;
                 CMPC_ROLLED
                 for (int i = lane; i < N * PS; i += NT) {
                     const double sl = lo[i], su = up[i], s = slp[i], y = yp[i], dy = dyp[i], zl0 = zlp[i], dl = dzl[i], zu0 = zup[i], du = dzu[i];
@@ -1069,8 +1108,8 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
                     const bool ineq = (hl || hu) && !(sl == su);
                     yp[i] = y + alpha * dy;
                     const double rl = 1.0 / (s - sl), ru = 1.0 / (su - s);  // one division per bound (footprint: an IEEE division is ~35 instructions)
-                    const double zl1 = fmax(fmin(zl0 + az * dl, (KAPPA_SIGMA * mu) * rl), (mu / KAPPA_SIGMA) * rl);
-                    const double zu1 = fmax(fmin(zu0 + az * du, (KAPPA_SIGMA * mu) * ru), (mu / KAPPA_SIGMA) * ru);
+                    const double zl1 = fmax(fmin(zl0 + az * dl, (KAPPA_SIGMA * mu_u) * rl), (mu_u / KAPPA_SIGMA) * rl);
+                    const double zu1 = fmax(fmin(zu0 + az * du, (KAPPA_SIGMA * mu_u) * ru), (mu_u / KAPPA_SIGMA) * ru);
                     if (ineq && hl) zlp[i] = zl1;
                     if (ineq && hu) zup[i] = zu1;
                 }
@@ -1082,6 +1121,8 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
         if (act) printf("it %3d f %.10e E0 %.2e (d %.2e v %.2e) mu %.2e dw %.1e alpha %.3e az %.3e rho %.1e rf %d pc %d\n", it, f, E0, ks.dual, ks.viol, mu, dw, alpha, az, ss.rho, rf, (int)pc);
 #endif
         if (act) ++it;
+        // IPOPT stops at a point that passes the acceptable-level test when the algorithm cannot continue from it
+        if ((fin == 2 || fin == 3) && nacc > 0) fin = 5;
         // an instance the predictor-corrector path cannot finish starts again from its initial point on the monotone path
         // (an exhausted ipopt_max_iteration is final, as in IPOPT: only the predictor-corrector's own iteration cap hands over)
         if (pc && (fin == 2 || fin == 3 || (fin == 1 && it < cfg.max_iter))) { pc = false; redo = true; it_base += it; fin = -1; }

@@ -147,8 +147,24 @@ template <int NT, int G> struct TeamCta { using type = DevCta; };
 template <> struct TeamCta<32, 1> { using type = DevWarp; };
 
 // G teams of NT threads per CTA, walking through the phases of their solves in lock-step (cmpc_ipm.cuh: ipm_run)
+// Register budget.  __launch_bounds__(672, 1) makes ptxas assume the block size rounded up to the next multiple of 128 (768
+// threads -> 80 registers, ~900 bytes of spills per thread on a kernel whose carve-out leaves no L1 behind the local memory);
+// the register file holds 21 warps x 96 registers, so the budget is stated directly (__maxnreg__, CUDA 12.4+).
+#ifndef CMPC_USE_MAXNREG
+#define CMPC_USE_MAXNREG 1
+#endif
+constexpr int team_kernel_regs(int nt, int g, int ctas)
+{
+    const int r = (65536 / (nt * g * ctas)) / 8 * 8;
+    return r > 255 ? 255 : r;
+}
+#if CMPC_USE_MAXNREG
+#define CMPC_KERNEL_BOUNDS(NT, G, CTAS) __maxnreg__(team_kernel_regs(NT, G, CTAS))
+#else
+#define CMPC_KERNEL_BOUNDS(NT, G, CTAS) __launch_bounds__(NT * G, CTAS)
+#endif
 template <int NT, int G, int CTAS>
-__global__ void __launch_bounds__(NT * G, CTAS)
+__global__ void CMPC_KERNEL_BOUNDS(NT, G, CTAS)
 cmpc_solve_team_kernel(const __grid_constant__ Config cfg, int batch, const double* __restrict__ p,
                        const double* __restrict__ lbg, const double* __restrict__ ubg, double* x, double* lam, double* obj,
                        int* status, int* iters, int warm_duals, double* work, size_t work_stride, unsigned int* counter,
@@ -459,6 +475,7 @@ int cmpc_default_config(cmpc_config* c)
     c->bound_push = 0.01; c->infinity = 1e19; c->device = 0; c->threads_per_instance = 0; c->ctas_per_sm = 0;
     c->mu_strategy = CMPC_MU_DEFAULT;
     c->warm_start_mu_init = 0.01;
+    c->nlp_scaling_max_gradient = 100.0; c->acceptable_tol = 1e-6; c->acceptable_iter = 15;
     return CMPC_OK;
 }
 
@@ -526,6 +543,9 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
     c.inf_bound = u->infinity > 0 ? u->infinity : 1e19;
     if (u->mu_strategy < 0 || u->mu_strategy > CMPC_MU_MEHROTRA) { delete h; return CMPC_E_INVALID; }
     c.pc = u->mu_strategy == CMPC_MU_MONOTONE ? 0 : 1;
+    c.scal_max_grad = u->nlp_scaling_max_gradient == 0.0 ? 100.0 : (u->nlp_scaling_max_gradient > 0.0 ? u->nlp_scaling_max_gradient : 0.0);
+    c.acc_tol = u->acceptable_tol == 0.0 ? 1e-6 : (u->acceptable_tol > 0.0 ? u->acceptable_tol : 0.0);
+    c.acc_iter = u->acceptable_iter > 0 ? u->acceptable_iter : 15;
     h->device = u->device;
     DeviceGuard guard(h->device);
     cudaError_t e = guard.err;

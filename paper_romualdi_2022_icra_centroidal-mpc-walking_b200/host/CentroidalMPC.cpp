@@ -163,6 +163,9 @@ bool CentroidalMPC::Impl::loadParameters(const ParametersHandler::IParametersHan
     h.getParameter("ipopt_tolerance", cfg.ipopt_tolerance);
     int maxIter = 0;
     if (h.getParameter("ipopt_max_iteration", maxIter) && maxIter > 0) cfg.ipopt_max_iteration = maxIter;
+    h.getParameter("nlp_scaling_max_gradient", cfg.nlp_scaling_max_gradient);  // additions: IPOPT option names, IPOPT defaults
+    h.getParameter("acceptable_tol", cfg.acceptable_tol);
+    h.getParameter("acceptable_iter", cfg.acceptable_iter);
     h.getParameter("solver_verbosity", verbosity);
     h.getParameter("is_warm_start_enabled", warmStartEnabled);
     h.getParameter("step_adjustment_enabled", stepAdjustmentEnabled);  // addition: false = every step box has zero width
@@ -489,7 +492,8 @@ bool CentroidalMPC::advanceBatch(const std::vector<CentroidalMPC*>& controllers)
         I.x.assign(X.begin() + b * L.n(), X.begin() + (b + 1) * L.n());
         I.lam.assign(LAM.begin() + b * L.m(), LAM.begin() + (b + 1) * L.m());
         I.stats.status = status[b]; I.stats.iterations = iters[b]; I.stats.objective = obj[b];
-        if (status[b] != CMPC_STATUS_CONVERGED) {  // IPOPT failure => CasADi throws => BLF returns false
+        // IPOPT failure => CasADi throws => BLF returns false; "Solved To Acceptable Level" counts as success for CasADi
+        if (status[b] != CMPC_STATUS_CONVERGED && status[b] != CMPC_STATUS_ACCEPTABLE) {
             I.fail("advance: the solver did not converge (status " + std::to_string(status[b]) + ")");
             ok = false;
             continue;

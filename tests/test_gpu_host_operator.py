@@ -13,9 +13,12 @@ torch = pytest.importorskip("torch")
 DATA = os.path.join(ROOT, "tests", "data")
 
 
-def setup(H, workloads, phase, seed=11, noise=1.0):
+def setup(H, workloads, phase, seed=11, noise=1.0, ini=None):
     w = workloads.walk_batch(N=12, B=1, seed=seed, phase=phase, state_noise=noise)
-    m = H.CentroidalMPCHost(os.path.join(DATA, "ergocub", "centroidal_mpc_walking.ini"), "TRAJECTORY_ADJUSTMENT/CENTROIDAL_MPC")
+    if ini is not None:
+        m = H.CentroidalMPCHost(ini, "")
+    else:
+        m = H.CentroidalMPCHost(os.path.join(DATA, "ergocub", "centroidal_mpc_walking.ini"), "TRAJECTORY_ADJUSTMENT/CENTROIDAL_MPC")
     L, p = m.L, w["p"][0]
     g0 = L.p_glob()
     assert m.set_state(p[g0:g0 + 3], p[g0 + 3:g0 + 6], p[g0 + 6:g0 + 9])
@@ -24,30 +27,46 @@ def setup(H, workloads, phase, seed=11, noise=1.0):
     return m, w
 
 
-def test_advance_matches_oracle(oracle, workloads):
+@pytest.mark.parametrize("tol", [1e-4, 1e-8], ids=["ini-tolerance", "tight"])
+def test_advance_matches_oracle(oracle, workloads, tol, tmp_path):
+    """advance() of the drop-in class against the oracle at the ini's own ipopt_tolerance (1e-4: both sides stop early, loose
+    bounds) and at 1e-8 (the boundary bar: objective 1e-6 relative, trajectories / forces / footsteps 1e-5)"""
     H = pkg("host")
-    m, w = setup(H, workloads, phase=5)
+    ini = None
+    if tol != 1e-4:
+        src = open(os.path.join(DATA, "ergocub", "centroidal_mpc.ini")).read()
+        assert "ipopt_tolerance                 1e-4" in src
+        ini = str(tmp_path / "centroidal_mpc.ini")
+        open(ini, "w").write(src.replace("ipopt_tolerance                 1e-4", f"ipopt_tolerance                 {tol:g}"))
+    m, w = setup(H, workloads, phase=5, ini=ini)
+    assert abs(m.config().ipopt_tolerance - tol) < 1e-20
     assert m.advance(), m.last_error()
     assert m.is_output_valid()
     st, it, obj = m.stats()
     o = make_cfg(N=12, w_pos=2000.0)
     O = oracle
-    xo, lo, so = O.solve_batch(o, w["p"], w["lbg"], w["ubg"], w["x0"], threads=1, opts=O.default_opts(tol=1e-4))
+    xo, lo, so = O.solve_batch(o, w["p"], w["lbg"], w["ubg"], w["x0"], threads=1, opts=O.default_opts(tol=tol))
     assert st == 0 and so[0].status == 0
-    assert abs(obj - so[0].obj) <= 1e-4 * max(1.0, abs(so[0].obj))     # both stop at the ini's ipopt_tolerance 1e-4
+    tight = tol <= 1e-8
+    assert abs(obj - so[0].obj) <= (1e-6 if tight else 1e-4) * max(1.0, abs(so[0].obj))
     L = m.L
     com, dcom, h = m.trajectories()
-    assert np.max(np.abs(com.reshape(-1) - xo[0][:39])) < 1e-3
+    assert np.max(np.abs(com.reshape(-1) - xo[0][:39])) < (1e-5 if tight else 1e-3)
+    assert np.max(np.abs(dcom.reshape(-1) - xo[0][39:78])) < (1e-5 if tight else 1e-2)
+    assert np.max(np.abs(h.reshape(-1) - xo[0][78:117])) < (1e-5 if tight else 1e-2)
     # knot-0 corner forces: right foot is in swing at phase 5 -> zero; left foot carries the weight
     posl, Rl, fl = m.contact_output("left_foot")
     posr, Rr, fr = m.contact_output("right_foot")
     assert np.all(fr == 0.0)
-    assert abs(fl[:, 2].sum() - xo[0][[L.x_frc(0, j, 0) + 2 for j in range(4)]].sum()) < 1e-2
+    fo = np.array([xo[0][L.x_frc(0, j, 0):L.x_frc(0, j, 0) + 3] for j in range(4)])
+    assert abs(fl[:, 2].sum() - fo[:, 2].sum()) < (1e-5 * 9.81 if tight else 1e-2)
+    if tight:
+        assert np.max(np.abs(fl - fo)) <= 1e-5 * max(1.0, np.max(np.abs(fo)))     # ergoCub: symmetry weight > 0, unique split
     # the right foot lands inside the horizon: its adjusted position is reported and edited into the phase list
     nxt = m.next_planned_contact("right_foot")
     assert nxt is not None
     land = int(round(nxt[1] / 0.1))
-    assert np.allclose(nxt[0], xo[0][L.x_pos(1, land + 1):L.x_pos(1, land + 1) + 3], atol=1e-3)
+    assert np.allclose(nxt[0], xo[0][L.x_pos(1, land + 1):L.x_pos(1, land + 1) + 3], atol=1e-5 if tight else 1e-3)
     lst = m.output_contact_list("right_foot")
     assert any(abs(c[0] - nxt[1]) < 1e-12 and np.allclose(c[2], nxt[0]) for c in lst)
     assert abs(m.current_time() - 0.1) < 1e-15                          # one sampling time per advance()

@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import pkg
+from conftest import have_ref, pkg
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
@@ -42,13 +42,40 @@ def groups(L):
     return g
 
 
-def compare_solutions(L, x, xo, obj, obj_o, forces=True):
+ICUB_CORNERS = np.array(ICUB_ORACLE["corners"][0], dtype=np.float64)
+ERGOCUB_CORNERS = np.array([(0.08, 0.01, 0), (0.08, -0.01, 0), (-0.08, -0.01, 0), (-0.08, 0.01, 0)], dtype=np.float64)
+
+
+def foot_wrenches(L, x, p, corners):
+    """(N, 2, 6): resultant force and torque about the foot origin of the corner forces of every contact at every knot --
+    what the dynamics see of the forces, and at knot 0 what the reference's whole-body layer consumes
+    (WholeBodyQPBlock.cpp:1084, 1121: the corner forces are summed into one contact wrench per foot)"""
+    N = L.N
+    out = np.zeros((N, 2, 6))
+    for k in range(N):
+        for c in range(2):
+            R = p[L.p_rot(c, k):L.p_rot(c, k) + 9].reshape(3, 3).T
+            en = p[L.p_en(c, k)]
+            for j in range(4):
+                f = en * x[L.x_frc(c, j, k):L.x_frc(c, j, k) + 3]
+                out[k, c, :3] += f
+                out[k, c, 3:] += np.cross(R @ corners[j], f)
+    return out
+
+
+def compare_solutions(L, x, xo, obj, obj_o, forces=True, p=None, corners=None):
+    """objective 1e-6 relative, every variable group 1e-5 scaled inf-norm.  forces=False (iCub3: no symmetry weight, the
+    split of a foot's wrench over its corners is not unique): the per-foot resultant wrenches of every knot instead"""
     assert abs(obj - obj_o) <= 1e-6 * max(1.0, abs(obj_o)), (obj, obj_o)
     for name, idx in groups(L).items():
         if name == "forces" and not forces:
             continue
         err = np.max(np.abs(x[idx] - xo[idx])) / max(1.0, np.max(np.abs(xo[idx])))
         assert err <= 1e-5, (name, err)
+    if not forces:
+        wa, wb = foot_wrenches(L, x, p, corners), foot_wrenches(L, xo, p, corners)
+        err = np.max(np.abs(wa - wb)) / max(1.0, np.max(np.abs(wb)))
+        assert err <= 1e-5, ("per-foot wrench", err)
 
 
 STRATEGIES = ["mehrotra", "monotone"]   # cmpc_config.mu_strategy; the oracle runs the same barrier update (opts.mehrotra)
@@ -160,16 +187,49 @@ def test_solve_batch_matches_oracle_icub3_no_step_adjustment(oracle, workloads, 
     # contact_force_symmetry_weight is 0 in the iCub3 ini: the split of a foot's wrench over its corners is not unique, and
     # rounding-level differences between the two implementations of the corrector solve (refinement sweep here, second
     # banded solve in the oracle) move along that flat set.  The monotone path tracks the oracle's iterates closely
-    # enough for the corner forces to agree too; for the predictor-corrector the resultants (trajectories) are compared.
+    # enough for the corner forces to agree too; for the predictor-corrector what IS unique is asserted: the per-foot resultant
+    # force and torque of every knot (what the dynamics and the reference's whole-body layer see) and the trajectories.
     for b in range(48):
-        compare_solutions(s.L, x[b], xo[b], obj[b], st[b].obj, forces=(strategy == "monotone"))
+        compare_solutions(s.L, x[b], xo[b], obj[b], st[b].obj, forces=(strategy == "monotone"), p=w["p"][b], corners=ICUB_CORNERS)
     s.close()
 
 
-def test_kkt_conditions_through_oracle_functions(solver12, oracle, workloads):
-    """optimality of the GPU solution measured with the ORACLE's f/g/jac (i.e. independent of the CUDA derivatives)"""
+def reference_nlp():
+    """the reference's own CasADi-generated functions (tmp.c compiled in place into oracle/_ref by oracle/Makefile; the
+    prebuilt library travels to the GPU box with the snapshot).  A box without it fails loudly: the KKT certificate below is
+    only worth something when it comes from the reference's code."""
+    from oracle.oracle import RefNLP
+    assert have_ref(), "oracle/_ref/libref_tmp.so is missing: run `make -C oracle ref` where /root/reference exists"
+    return RefNLP("tmp")
+
+
+def kkt_certificate(fn, jc, jr, x, lam, p, lbg, ubg, obj, n=555, m=651):
+    """KKT conditions of (x, lam) evaluated with the functions `fn` (jac_fg): scaled stationarity, feasibility, objective,
+    multiplier signs"""
+    f, grad, g, jnz = fn(x, p)
+    r = grad.copy()
+    for c in range(n):
+        sl = slice(jc[c], jc[c + 1])
+        r[c] += np.dot(jnz[sl], lam[jr[sl]])
+    scale = max(100.0, np.sum(np.abs(lam)) / m) / 100.0
+    assert np.max(np.abs(r)) / scale < 1e-7, np.max(np.abs(r))
+    viol = np.maximum(np.maximum(lbg - g, g - ubg), 0.0)
+    assert viol.max() < 4e-8                               # bounds are relaxed by 1e-8 (bound_relax_factor)
+    assert abs(f - obj) <= 1e-10 * abs(f)
+    ineq = ubg > lbg
+    assert np.all(np.abs(lam[ineq & (g < ubg - 1e-3) & (g > lbg + 1e-3)]) < 1e-4)   # mu / slack
+    assert np.all(lam[ineq & (ubg > 1e19)] <= 1e-12) and np.all(lam[ineq & (lbg < -1e19)] >= -1e-12)
+
+
+def test_kkt_conditions_through_reference_functions(solver12, oracle, workloads):
+    """optimality of the GPU solution certified with the REFERENCE's own generated code (nlp_jac_fg of tmp.c, compiled into
+    oracle/_ref/libref_tmp.so: N = 12, contact_position_weight 200) and, second, with the oracle's restatement of it"""
+    ref = reference_nlp()
     w = workloads.walk_batch(N=12, B=16, seed=3, state_noise=1.5, yaw_range=0.2)
     x, lam, obj, status, iters = solver12.solve_host(w["p"], w["lbg"], w["ubg"], w["x0"])
+    assert (status == 0).all()
+    for b in range(16):
+        kkt_certificate(ref.jac_fg, ref.jc, ref.jr, x[b], lam[b], w["p"][b], w["lbg"][b], w["ubg"][b], obj[b])
     cfg = make_cfg()
     jc, jr = oracle.jac_sparsity(12)
     for b in range(16):
@@ -355,6 +415,10 @@ def test_predictor_corrector_lands_on_the_monotone_optimum(oracle, workloads, ro
             assert np.max(np.abs(x[b][idx] - xo[b][idx])) / max(1.0, np.max(np.abs(xo[b][idx]))) <= 1e-5, (b, name)
         idx = g["forces"]
         same_forces += np.max(np.abs(x[b][idx] - xo[b][idx])) / max(1.0, np.max(np.abs(xo[b][idx]))) <= 1e-5
+        # what IS unique, and what the reference consumes: the per-foot resultant force / torque (every knot, incl. knot 0)
+        corners = ERGOCUB_CORNERS if robot == "ergocub" else ICUB_CORNERS
+        wa, wb = foot_wrenches(s.L, x[b], w["p"][b], corners), foot_wrenches(s.L, xo[b], w["p"][b], corners)
+        assert np.max(np.abs(wa - wb)) / max(1.0, np.max(np.abs(wb))) <= 1e-5, (b, "per-foot wrench")
     it_o = np.mean([q.iters for q in st])
     print(f"{robot}: corner forces equal to the monotone optimum in {same_forces}/64 instances; iterations {iters.mean():.1f} vs {it_o:.1f}")
     if robot == "ergocub":
@@ -387,6 +451,16 @@ def test_full_size_ergocub_shard_properties(oracle, workloads):
         err = np.max(np.abs(xm[:, idx] - xq[:, idx]), axis=1) / np.maximum(1.0, np.max(np.abs(xq[:, idx]), axis=1))
         assert err.max() <= 1e-5, (name, err.max(), int(err.argmax()))
     assert itm.mean() < 0.75 * itq.mean()
+    # the same shard with the weight set baked into the reference's tmp.c (contact_position_weight 200): every 16th instance
+    # certified with the reference's own generated functions
+    ref = reference_nlp()
+    s = P.BatchedCentroidalMPC(P.ergocub_config(contact_position_weight=200.0))
+    sub = slice(0, B, 16)
+    xr, lr, or_, str_, itr = s.solve_host(w["p"][sub], w["lbg"][sub], w["ubg"][sub], w["x0"][sub])
+    s.close()
+    assert (str_ == 0).all(), np.bincount(str_)
+    for i, b in enumerate(range(0, B, 16)):
+        kkt_certificate(ref.jac_fg, ref.jc, ref.jr, xr[i], lr[i], w["p"][b], w["lbg"][b], w["ubg"][b], or_[i])
     cfg = make_cfg(w_pos=2000.0)
     jc, jr = oracle.jac_sparsity(12)
     for b in range(0, B, 512):
@@ -479,3 +553,57 @@ def test_iteration_limit_is_final(workloads, strategy):
     s.close()
     assert (status == 1).all() and (iters == 5).all(), (status, iters)
     assert np.isfinite(x).all() and np.any(x != w["x0"])
+
+
+def test_long_horizon_auxiliary_kernels(oracle):
+    """horizons above 115 / 152 knots need more than 48 KB of dynamic shared memory in the shift / evaluation kernels (opted in
+    by cmpc_create): N = 160 evaluates f, g, grad f like the oracle and shifts like numpy"""
+    P = pkg()
+    N = 160
+    s = P.BatchedCentroidalMPC(P.ergocub_config(horizon=N, contact_position_weight=200.0))
+    cfg = make_cfg(N=N)
+    d = oracle.dims(N)
+    rng = np.random.default_rng(N)
+    x, p = rng.normal(size=(2, d["n"])), rng.normal(size=(2, d["np"]))
+    f, grad, g, _ = s.eval_jac_fg(dev(x), dev(p), want_jac=False)
+    torch.cuda.synchronize()
+    for b in range(2):
+        fo, grado, go, jo = oracle.jac_fg(cfg, x[b], p[b])
+        assert abs(f[b].item() - fo) <= 1e-12 * abs(fo)
+        assert rel(g[b].cpu().numpy(), go) < 1e-12 and rel(grad[b].cpu().numpy(), grado) < 1e-12
+    L = s.L
+    lam = rng.normal(size=(2, L.m))
+    dx, dl = dev(x), dev(lam)
+    s.shift_warmstart(dx, dl)
+    torch.cuda.synchronize()
+    xs, ls = dx.cpu().numpy(), dl.cpu().numpy()
+    for b in range(2):
+        for blk, cols in ((0, N + 1), (L.x_h(0), N + 1), (L.x_pos(1, 0), N + 1), (L.x_vel(0, 0), N), (L.x_frc(1, 3, 0), N)):
+            a = x[b, blk:blk + 3 * cols].reshape(cols, 3)
+            assert np.array_equal(xs[b, blk:blk + 3 * cols].reshape(cols, 3), np.vstack([a[1:], a[-1:]]))
+        a = lam[b, L.g_fric(0, 0, 0):L.g_fric(0, 0, 0) + 16 * N].reshape(N, 16)
+        assert np.array_equal(ls[b, L.g_fric(0, 0, 0):L.g_fric(0, 0, 0) + 16 * N].reshape(N, 16), np.vstack([a[1:], a[-1:]]))
+    s.close()
+
+
+def test_two_streams_on_one_handle_are_ordered(workloads):
+    """a handle owns one work queue and one scratch arena: two solves enqueued on different streams without any
+    synchronisation by the caller are serialised by the library and give the results of two separate calls"""
+    P = pkg()
+    s = P.BatchedCentroidalMPC(P.ergocub_config(teams_per_cta=7))
+    w1 = workloads.walk_batch(N=12, B=300, seed=41, state_noise=1.5, yaw_range=0.2)
+    w2 = workloads.walk_batch(N=12, B=300, seed=42, state_noise=1.5, yaw_range=0.2)
+    ref = [s.solve_host(w["p"], w["lbg"], w["ubg"], w["x0"]) for w in (w1, w2)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    dx, out = [], []
+    torch.cuda.synchronize()
+    for w, st in zip((w1, w2), streams):
+        with torch.cuda.stream(st):
+            x = dev(w["x0"])
+            out.append(s.solve(dev(w["p"]), dev(w["lbg"]), dev(w["ubg"]), x))
+            dx.append(x)
+    torch.cuda.synchronize()
+    for i in range(2):
+        assert (out[i][1].cpu().numpy() == 0).all()
+        assert np.array_equal(dx[i].cpu().numpy(), ref[i][0]) and np.array_equal(out[i][2].cpu().numpy(), ref[i][4])
+    s.close()
