@@ -147,24 +147,11 @@ template <int NT, int G> struct TeamCta { using type = DevCta; };
 template <> struct TeamCta<32, 1> { using type = DevWarp; };
 
 // G teams of NT threads per CTA, walking through the phases of their solves in lock-step (cmpc_ipm.cuh: ipm_run)
-// Register budget.  __launch_bounds__(672, 1) makes ptxas assume the block size rounded up to the next multiple of 128 (768
-// threads -> 80 registers, ~900 bytes of spills per thread on a kernel whose carve-out leaves no L1 behind the local memory);
-// the register file holds 21 warps x 96 registers, so the budget is stated directly (__maxnreg__, CUDA 12.4+).
-#ifndef CMPC_USE_MAXNREG
-#define CMPC_USE_MAXNREG 1
-#endif
-constexpr int team_kernel_regs(int nt, int g, int ctas)
-{
-    const int r = (65536 / (nt * g * ctas)) / 8 * 8;
-    return r > 255 ? 255 : r;
-}
-#if CMPC_USE_MAXNREG
-#define CMPC_KERNEL_BOUNDS(NT, G, CTAS) __maxnreg__(team_kernel_regs(NT, G, CTAS))
-#else
-#define CMPC_KERNEL_BOUNDS(NT, G, CTAS) __launch_bounds__(NT * G, CTAS)
-#endif
+// Register budget: registers are allocated to groups of 4 warps, so the 21 warps of the seven-team CTA occupy 24 warp slots
+// and the budget is 65536 / 768 = 85 -> 80 registers per thread (what ptxas derives from __launch_bounds__(672, 1); a kernel
+// built with __maxnreg__(96) does not launch).  An eighth team of 96 threads would be free in registers.
 template <int NT, int G, int CTAS>
-__global__ void CMPC_KERNEL_BOUNDS(NT, G, CTAS)
+__global__ void __launch_bounds__(NT * G, CTAS)
 cmpc_solve_team_kernel(const __grid_constant__ Config cfg, int batch, const double* __restrict__ p,
                        const double* __restrict__ lbg, const double* __restrict__ ubg, double* x, double* lam, double* obj,
                        int* status, int* iters, int warm_duals, double* work, size_t work_stride, unsigned int* counter,
