@@ -298,17 +298,19 @@ def run_config4(pkg, dev, local, rank, world, total=4096, ticks=100):
     R = importlib.import_module(PKG + ".rollout")
     sharding = importlib.import_module(PKG + ".sharding")
     B = total // world
-    out = {"rollouts_total": B * world, "rollouts_per_gpu": B, "ticks": ticks, "scaling": "strong", "robot_ini": "ergoCubGazeboV1_1/centroidal_mpc.ini"}
+    out = {"rollouts_total": B * world, "rollouts_per_gpu": B, "ticks": ticks, "scaling": "strong", "robot_ini": "ergoCubGazeboV1_1/centroidal_mpc.ini",
+           "driver": "rollout.closed_loop_rollout_device: six library kernels per tick (tick records, populate, shift, solve, plant, "
+                     "feedback), ticks 1 .. T - 1 = one captured CUDA graph replayed; wall time includes set-up, capture and the final gather"}
     for tol in (1e-4, 1e-8):
         cfg = pkg.ergocub_config()
         cfg.device, cfg.ipopt_tolerance = local, tol
         solver = pkg.BatchedCentroidalMPC(cfg)
-        R.closed_loop_rollout(solver, B=B, ticks=4, seed=rank)          # warm-up (allocator, kernels, tables)
+        R.closed_loop_rollout_device(solver, B=B, ticks=4, seed=rank)   # warm-up (allocator, kernels, graph capture)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        res = R.closed_loop_rollout(solver, B=B, ticks=ticks, seed=100 + rank, time_device=True)
+        res = R.closed_loop_rollout_device(solver, B=B, ticks=ticks, seed=100 + rank, time_device=True)
         local_stats = torch.from_numpy(np.stack([res["converged_ticks"], res["iterations"]], axis=1).astype(np.float64)).to(dev)
         allres = sharding.gather_results(local_stats, world)
         torch.cuda.synchronize()
@@ -376,6 +378,7 @@ def main():
     ap.add_argument("--identical", action="store_true", help="experiment: every instance is a copy of instance 0")
     ap.add_argument("--ctas", type=int, default=0, help="resident teams per SM (0 = occupancy)")
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (0 = the workload's own size)")
+    ap.add_argument("--batches", type=int, default=8, help="different synthetic batches per rank the timed steps cycle through")
     ap.add_argument("--mu-strategy", default="mehrotra", choices=["mehrotra", "monotone"],
                     help="barrier update of the solve: Mehrotra predictor-corrector (library default) or IPOPT's monotone update")
     args = ap.parse_args()
@@ -400,10 +403,17 @@ def main():
     pkg = importlib.import_module(PKG)
     wl = importlib.import_module(PKG + ".workloads")
     sharding = importlib.import_module(PKG + ".sharding")
-    cfg, w, ocfg = workload(args.workload, pkg, wl, seed=rank, batch=args.batch)   # every rank its own shard of instances
+    # every rank its own instances; the timed steps cycle through NB different batches (seeds rank * NB .. rank * NB + NB - 1):
+    # a single-wave launch lasts as long as its unluckiest SM (seven instances sharing lock-step groups), which makes the time
+    # of ONE batch of 1024 vary by +-5 % with the draw (16.5 ms for seed 0, 18.2 ms for seed 1 at the same mean and maximum
+    # iteration count); a number measured on one draw is luck, and the ratio of two such numbers is not a scaling efficiency
+    NB = max(1, min(args.steps, args.batches))
+    ws = [workload(args.workload, pkg, wl, seed=rank * NB + j, batch=args.batch) for j in range(NB)]
+    cfg, w, ocfg = ws[0]
     if args.identical:
-        for key in ("p", "lbg", "ubg", "x0"):
-            w[key] = np.repeat(w[key][:1], w[key].shape[0], axis=0)
+        for _, wj, _ in ws:
+            for key in ("p", "lbg", "ubg", "x0"):
+                wj[key] = np.repeat(wj[key][:1], wj[key].shape[0], axis=0)
     cfg.device = local
     cfg.ipopt_tolerance = args.tol
     cfg.threads_per_instance = args.team
@@ -415,7 +425,8 @@ def main():
     B, N = w["p"].shape[0], cfg.horizon
     n, m, npar = solver.L.n, solver.L.m, solver.L.np
     tens = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
-    d_p, d_lbg, d_ubg, d_x0 = tens(w["p"]), tens(w["lbg"]), tens(w["ubg"]), tens(w["x0"])
+    dws = [tuple(tens(wj[k]) for k in ("p", "lbg", "ubg", "x0")) for _, wj, _ in ws]   # device-resident inputs of every batch
+    d_p, d_lbg, d_ubg, d_x0 = dws[0]
     d_x = d_x0.clone()
     d_lam = torch.zeros(B, m, dtype=torch.float64, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2
@@ -429,10 +440,11 @@ def main():
     gather = sharding.AsyncGather(world) if per_step else None
     results = torch.zeros(args.steps, B, 3, dtype=torch.float64, device=dev)
 
-    for _ in range(args.warmup):
+    for j in range(args.warmup):
         flush.zero_()
-        d_x.copy_(d_x0)
-        obj, status, iters, _ = solver.solve(d_p, d_lbg, d_ubg, d_x, d_lam)
+        bp, bl, bu, bx = dws[j % NB]
+        d_x.copy_(bx)
+        obj, status, iters, _ = solver.solve(bp, bl, bu, d_x, d_lam)
         if per_step:
             gather.submit(sharding.pack_results(obj, status, iters))
     if per_step:
@@ -453,10 +465,11 @@ def main():
     t_wall0 = time.perf_counter()
     for s in range(args.steps):
         flush.zero_()                      # L2 flush between timed iterations (outside the step's event pair)
+        bp, bl, bu, bx = dws[s % NB]
         ev[s][0].record()
-        d_x.copy_(d_x0)
+        d_x.copy_(bx)
         kev[s][0].record()
-        obj, status, iters, _ = solver.solve(d_p, d_lbg, d_ubg, d_x, d_lam)
+        obj, status, iters, _ = solver.solve(bp, bl, bu, d_x, d_lam)
         kev[s][1].record()
         if per_step:
             gather.submit(sharding.pack_results(obj, status, iters))
@@ -484,9 +497,15 @@ def main():
     t_dev = t_steps + tail[0].elapsed_time(tail[1]) * 1e-3
     t_kernel = sum(a.elapsed_time(b) for a, b in kev) * 1e-3
     t_max = max_over_ranks(t_dev, dev, world)
-    status_h, iters_h = status.cpu().numpy(), iters.cpu().numpy()
+    if per_step:
+        res_all = torch.cat([sharding.pack_results(obj, status, iters)] * args.steps).view(args.steps, B, 3)   # last step only
+    else:
+        res_all = results
+    status_all, iters_all = res_all[:, :, 1].cpu().numpy(), res_all[:, :, 2].cpu().numpy()     # (steps, B) of this rank
+    status_h, iters_h = status_all.reshape(-1), iters_all.reshape(-1)
     conv = int((status_h == 0).sum())
     total_iters = int(iters_h.sum())
+    step_ms = [a.elapsed_time(b) for a, b in kev]
     # per-rank record: kernel time per launch, own steps without the final gather, iteration statistics
     mine = torch.tensor([1e3 * t_kernel / args.steps, 1e3 * t_steps / args.steps, float(iters_h.mean()), float(iters_h.max()),
                          float(conv)], dtype=torch.float64, device=dev)
@@ -515,31 +534,34 @@ def main():
 
     # ---- end to end through the host-pointer C-ABI call with pinned host buffers
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
-    h_p, h_lbg, h_ubg, h_x0 = pin(w["p"]), pin(w["lbg"]), pin(w["ubg"]), pin(w["x0"])
+    hws = [tuple(pin(wj[k]) for k in ("p", "lbg", "ubg", "x0")) for _, wj, _ in ws[:5]]
+    h_p, h_lbg, h_ubg, h_x0 = hws[0]
     h_x, h_lam = torch.empty_like(h_x0).pin_memory(), torch.zeros(B, m, dtype=torch.float64).pin_memory()
     h_obj = torch.zeros(B, dtype=torch.float64).pin_memory()
     h_st, h_it = torch.zeros(B, dtype=torch.int32).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory()
     import ctypes as C
     vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
 
-    def e2e_step(hx):
+    def e2e_step(hx, hw):
         # hx: pinned host buffer holding the step's initial guess on entry and the solution on return (the C ABI solves in
         # place); every timed step gets its own pre-filled buffer, so that the timed region is the call itself: H2D copies,
         # solve, D2H copies, synchronisation
-        rc = solver.lib.cmpc_solve_host(solver.handle, B, vp(h_p), vp(h_lbg), vp(h_ubg), vp(hx), vp(h_lam), vp(h_obj),
+        rc = solver.lib.cmpc_solve_host(solver.handle, B, vp(hw[0]), vp(hw[1]), vp(hw[2]), vp(hx), vp(h_lam), vp(h_obj),
                                         vp(h_st), vp(h_it), 0)
         assert rc == 0, rc
     h_x.copy_(h_x0)
-    e2e_step(h_x)
+    e2e_step(h_x, hws[0])
     torch.cuda.synchronize()
     k_e2e = max(2, min(args.steps, 5))
-    h_xs = [h_x0.clone().pin_memory() for _ in range(k_e2e - 1)] + [h_x]
+    # timed step j solves batch (j + 1) % len(hws); the last one is batch 0 into h_x (the parity report reads it)
+    order = [(j + 1) % len(hws) for j in range(k_e2e - 1)] + [0]
+    h_xs = [hws[b][3].clone().pin_memory() for b in order[:-1]] + [h_x]
     h_x.copy_(h_x0)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for j in range(k_e2e):
-        e2e_step(h_xs[j])
+        e2e_step(h_xs[j], hws[order[j]])
     torch.cuda.synchronize()
     e2e_value = world * B * k_e2e / max_over_ranks(time.perf_counter() - t0, dev, world)
     h2d = 8 * B * (npar + 2 * m + n)
@@ -576,8 +598,8 @@ def main():
     if rank == 0:
         value = world * B * args.steps / t_max
         kernel_s = t_kernel / args.steps
-        flop_exec = total_iters * N * FLOP_EXEC_PER_ITER_KNOT[args.mu_strategy]
-        flop_canon = total_iters * N * FLOP_CANON_PER_ITER_KNOT
+        flop_exec = total_iters / args.steps * N * FLOP_EXEC_PER_ITER_KNOT[args.mu_strategy]      # per launch (mean over the steps)
+        flop_canon = total_iters / args.steps * N * FLOP_CANON_PER_ITER_KNOT
         achieved = flop_exec / kernel_s / 1e12
         alg_bytes = 8.0 * B * (npar + 2 * m + 2 * n + 2 * m)
         line = {
@@ -585,14 +607,16 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(args.workload, B, N, args.tol),
-            "solve_stats": {"mu_strategy": args.mu_strategy, "converged": f"{conv}/{B}", "mean_iterations": total_iters / B,
-                            "solver_grid": geometry, "result_gather": args.gather},
+            "solve_stats": {"mu_strategy": args.mu_strategy, "converged": f"{conv}/{B * args.steps}",
+                            "mean_iterations": total_iters / (B * args.steps), "max_iterations": int(iters_h.max()),
+                            "solver_grid": geometry, "result_gather": args.gather, "different_batches": NB,
+                            "kernel_ms_of_every_step_rank0": [round(v, 3) for v in step_ms]},
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": k_e2e, "api": "cmpc_solve_host (pinned host buffers)"},
             "gpu_launches": int(launches),
             "latency": {"p50_single_solve_ms": float(np.median(lat)) if lat else None,
                         "p95_single_solve_ms": float(np.percentile(lat, 95)) if lat else None, "samples": len(lat),
-                        "iterations": int(iters_h[0]),
+                        "iterations": int(iters_all[0, 0]),
                         "e2e_host_operator_ms": (extras.get("config1_single_solve_host_operator") or {}).get("p50_ms"),
                         "note": "batch of one instance, device resident, cold start; batches of up to 4 instances per SM run on independent single-team CTAs (128 threads; up to 2 per SM without a register cap) unless a geometry is forced; e2e_host_operator_ms = CentroidalMPC::advance() of the drop-in class"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,

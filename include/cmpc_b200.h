@@ -19,7 +19,8 @@
  * Thread safety: calls on different handles are independent; a handle must not be used from two threads at once.
  * Stream semantics: a handle owns ONE work queue and ONE scratch arena, so it has at most one solve in flight: solves
  * enqueued on different streams are serialised by the library (an event recorded behind every solve; a solve on another
- * stream than the previous one waits for it on the device).  Use one handle per stream to overlap solves.  Every entry
+ * stream than the previous one waits for it on the device; calls made while the stream is captured into a CUDA graph are
+ * ordered by the graph's own stream).  Use one handle per stream to overlap solves.  Every entry
  * point runs on the handle's device and restores the caller's current device before it returns.
  */
 #ifndef CMPC_B200_H
@@ -99,6 +100,8 @@ typedef struct cmpc_config {
                                             /* scaled: their gradients are bounded far below 100              */
     double acceptable_tol;                  /* IPOPT acceptable_tol: 0 = IPOPT's default 1e-6, negative = off                        */
     int acceptable_iter;                    /* IPOPT acceptable_iter: 0 = IPOPT's default 15                                         */
+    double bounding_box_upper_limit[CMPC_NUM_CONTACTS][3]; /* CONTACT_c / bounding_box_upper_limit, _lower_limit: the step-adjustment */
+    double bounding_box_lower_limit[CMPC_NUM_CONTACTS][3]; /* box of a future contact, contact frame (used by cmpc_populate only)     */
 } cmpc_config;
 #define CMPC_MU_DEFAULT 0
 #define CMPC_MU_MONOTONE 1
@@ -143,6 +146,61 @@ int cmpc_solve_host(cmpc_handle h, int batch, const double* p, const double* lbg
 /* Warm-start shift between ticks (BLF is_warm_start_enabled): every knot-indexed block of x and lam_g moves one knot
  * towards the present, the last knot is repeated.  DEVICE pointers, in place.  d_lam_g may be null. */
 int cmpc_shift_warmstart(cmpc_handle h, int batch, double* d_x, double* d_lam_g, void* stream);
+
+/* ---- input population on the device: what setState / setReferenceTrajectory / setContactPhaseList do before a solve ------
+ * (CentroidalMPCBlock.cpp:407, :579, :609).  A TICK RECORD per instance holds the state, the external wrench, the references
+ * and, per foot, the contacts the horizon can see (times in nanoseconds relative to the instance's current time):
+ *      [0..8] com, dcom, angular momentum   [9..14] external force, torque   [15] 1 = step adjustment enabled   [16] reserved
+ *      [17 ..) CoM reference 3 (N + 1), angular-momentum reference 3 (N + 1)
+ *      per foot c at 17 + 6 (N + 1) + 85 c: [0] number of contacts n <= 6, then n x {t_on, t_off, position[3], rotation[9] column
+ *      major} in time order (window: the last contact activated at or before now, every later one up to the first that starts
+ *      after the horizon).  cmpc_tick_stride(N) = 6 N + 194 doubles.
+ * cmpc_populate expands records into the solver's formal input (same rules as the host operator; DEVICE pointers, d_x0 may be
+ * null).  cmpc_solve_ticks_host is the per-tick call of a host controller: HOST pointers; uploads the records (2.3 KB per
+ * instance instead of 24.7 KB of p / lbg / ubg / x0), populates, solves, downloads x (and lam_g when not null), obj, status,
+ * iters, and keeps the solution resident on the device.  warm_mode: 0 = cold start from the populated x0; 1 = warm start from
+ * the solution the previous call on this handle left on the device (same batch size), shifted by one knot; 2 = warm start from
+ * the x / lam_g passed in (the previous solution, NOT shifted: the shift runs on the device). */
+int cmpc_tick_stride(int horizon);
+int cmpc_populate(cmpc_handle h, int batch, const double* d_ticks, double* d_p, double* d_lbg, double* d_ubg, double* d_x0,
+                  void* stream);
+int cmpc_solve_ticks_host(cmpc_handle h, int batch, const double* ticks, int warm_mode, double* x, double* lam_g, double* obj,
+                          int* status, int* iters);
+
+/* Reference resampling on the device (the Math::LinearSpline frequency adapters of CentroidalMPCBlock.cpp:201-260, 525-577):
+ * n_in planner samples of CoM / angular momentum per instance (d_com_in, d_h_in: batch x n_in x 3) at the shared times d_t_in
+ * (increasing) -> the N + 1 reference knots at d_t_out (ordered), written into the tick records.  The angular momentum is
+ * divided by robot_mass (:525-529); com_height >= 0 overrides the CoM height (:531-535, 0.7 in the reference). */
+int cmpc_resample_references(cmpc_handle h, int batch, int n_in, const double* d_t_in, const double* d_com_in,
+                             const double* d_h_in, const double* d_t_out, double robot_mass, double com_height, double* d_ticks,
+                             void* stream);
+
+/* Desired ZMP of the knot-0 corner forces (computeDesiredZMP, WholeBodyQPBlock.cpp:805-873; the reference clamps the local ZMP
+ * to half_length 0.08 / half_width 0.03, :837-838).  d_zmp[batch][2]; d_valid[batch] (may be null) = 0 where no contact
+ * carries force.  DEVICE pointers. */
+int cmpc_desired_zmp(cmpc_handle h, int batch, const double* d_x, const double* d_p, double half_length, double half_width,
+                     double* d_zmp, int* d_valid, void* stream);
+
+/* ---- closed loop, device side (BASELINE config 4): a synthetic planner (the walk schedule of SURVEY.md 8(d)) keeps one
+ * footstep table per rollout; cmpc_rollout_tick writes the tick records of MPC tick `tick` (plant state, push, references,
+ * contact windows with the MPC's own landings: updateContactPhaseList, CentroidalMPCBlock.cpp:32-110) and the external wrench
+ * acting on the plant; cmpc_rollout_feedback accumulates the statistics and writes the landing position of a foot that touches
+ * down into the table.  d_roll[batch][roll_stride]: phase0, push tick / length / force[3], converged ticks, iterations, max
+ * CoM error, min CoM height, max ZMP excess, ticks done; d_steps[batch][2][max_steps][4] = x, y, z, yaw.  DEVICE pointers.
+ * tick < 0: the tick index is read from the rollout records (cmpc_rollout_feedback counts it up), so that the kernels of one
+ * tick can be captured into a CUDA graph once and replayed. */
+typedef struct cmpc_walk_params {
+    int ds_knots, ss_knots;                 /* double / single support duration in MPC knots                      */
+    double step_length, com_height;
+    double push_threshold;                  /* external forces below it are not reported to the MPC (0.7)           */
+    double zmp_half_length, zmp_half_width; /* clamp of the local ZMP (0.08, 0.03)                                  */
+} cmpc_walk_params;
+int cmpc_rollout_layout(int* roll_stride, int* max_steps, int* step_stride);
+int cmpc_rollout_tick(cmpc_handle h, const cmpc_walk_params* w, int batch, int tick, const double* d_roll, const double* d_state,
+                      const double* d_steps, double* d_ticks, double* d_ext6, int step_adjust, void* stream);
+int cmpc_rollout_feedback(cmpc_handle h, const cmpc_walk_params* w, int batch, int tick, const double* d_x, const double* d_p,
+                          const double* d_state, const int* d_status, const int* d_iters, double* d_roll, double* d_steps,
+                          void* stream);
 
 /* ---- the NLP functions themselves (parity surface for nlp_fg / nlp_jac_fg / nlp_hess_l of tmp.c) ------------------
  * DEVICE pointers, instance major; outputs may be null.  jac/hess nonzeros in the CasADi CSC order above. */

@@ -30,7 +30,14 @@ class CmpcConfig(C.Structure):
                 ("infinity", C.c_double), ("device", C.c_int), ("threads_per_instance", C.c_int),
                 ("ctas_per_sm", C.c_int), ("teams_per_cta", C.c_int), ("lockstep_groups", C.c_int),
                 ("mu_strategy", C.c_int), ("warm_start_mu_init", C.c_double), ("nlp_scaling_max_gradient", C.c_double),
-                ("acceptable_tol", C.c_double), ("acceptable_iter", C.c_int)]
+                ("acceptable_tol", C.c_double), ("acceptable_iter", C.c_int),
+                ("bounding_box_upper_limit", C.c_double * 6), ("bounding_box_lower_limit", C.c_double * 6)]
+
+
+class WalkParams(C.Structure):
+    """struct cmpc_walk_params of include/cmpc_b200.h: the synthetic planner of the closed loop"""
+    _fields_ = [("ds_knots", C.c_int), ("ss_knots", C.c_int), ("step_length", C.c_double), ("com_height", C.c_double),
+                ("push_threshold", C.c_double), ("zmp_half_length", C.c_double), ("zmp_half_width", C.c_double)]
 
 
 _dp = C.POINTER(C.c_double)
@@ -65,6 +72,14 @@ def load_library() -> C.CDLL:
     L.cmpc_eval_jac_fg.argtypes = [vp, i, vp, vp, vp, vp, vp, vp, vp]
     L.cmpc_eval_hess_l.argtypes = [vp, i, vp, vp, d, vp, vp, vp]
     L.cmpc_rollout_plant.argtypes = [vp, i, vp, vp, vp, vp, d, i, vp]
+    L.cmpc_tick_stride.argtypes = [i]
+    L.cmpc_populate.argtypes = [vp, i, vp, vp, vp, vp, vp, vp]
+    L.cmpc_solve_ticks_host.argtypes = [vp, i, vp, i, vp, vp, vp, vp, vp]
+    L.cmpc_resample_references.argtypes = [vp, i, i, vp, vp, vp, vp, d, d, vp, vp]
+    L.cmpc_desired_zmp.argtypes = [vp, i, vp, vp, d, d, vp, vp, vp]
+    L.cmpc_rollout_layout.argtypes = [_ip, _ip, _ip]
+    L.cmpc_rollout_tick.argtypes = [vp, C.POINTER(WalkParams), i, i, vp, vp, vp, vp, vp, i, vp]
+    L.cmpc_rollout_feedback.argtypes = [vp, C.POINTER(WalkParams), i, i, vp, vp, vp, vp, vp, vp, vp, vp]
     L.cmpc_measure_fp64_peak.argtypes = [vp, _dp]
     L.cmpc_launch_count.argtypes = [vp]
     L.cmpc_launch_count.restype = C.c_longlong
@@ -83,6 +98,8 @@ def default_config(**overrides) -> CmpcConfig:
     for k, v in overrides.items():
         if k in ("com_weight", "force_rate_of_change_weight"):
             getattr(cfg, k)[:] = list(v)
+        elif k in ("bounding_box_upper_limit", "bounding_box_lower_limit"):
+            getattr(cfg, k)[:] = np.asarray(v, dtype=np.float64).reshape(-1).tolist()
         elif k == "corners":
             cfg.corners[:] = np.asarray(v, dtype=np.float64).reshape(-1).tolist()
         else:
@@ -142,7 +159,8 @@ class BatchedCentroidalMPC:
     def _ptr(t):
         if t is None:
             return None
-        assert t.is_cuda and t.is_contiguous()
+        import torch
+        assert t.is_cuda and t.is_contiguous() and t.dtype in (torch.float64, torch.int32), (t.device, t.dtype)
         return C.c_void_p(t.data_ptr())
 
     def _stream(self):
@@ -166,13 +184,17 @@ class BatchedCentroidalMPC:
         return int(self.lib.cmpc_launch_count(self.handle))
 
     # ---- hot path
-    def solve(self, p, lbg, ubg, x, lam_g=None, warm_duals=False):
-        """In place on x (and lam_g).  Returns (obj, status, iters) device tensors.  Asynchronous."""
+    def solve(self, p, lbg, ubg, x, lam_g=None, warm_duals=False, out=None):
+        """In place on x (and lam_g).  Returns (obj, status, iters, lam_g) device tensors.  Asynchronous.  out = (obj, status,
+        iters) reuses caller-owned result tensors (CUDA-graph capture needs static buffers)."""
         import torch
         B = p.shape[0]
-        obj = torch.empty(B, dtype=torch.float64, device=self.device)
-        status = torch.empty(B, dtype=torch.int32, device=self.device)
-        iters = torch.empty(B, dtype=torch.int32, device=self.device)
+        if out is not None:
+            obj, status, iters = out
+        else:
+            obj = torch.empty(B, dtype=torch.float64, device=self.device)
+            status = torch.empty(B, dtype=torch.int32, device=self.device)
+            iters = torch.empty(B, dtype=torch.int32, device=self.device)
         if lam_g is None:
             lam_g = torch.zeros(B, self.L.m, dtype=torch.float64, device=self.device)
         _check(self.lib.cmpc_solve_batched(self.handle, B, self._ptr(p), self._ptr(lbg), self._ptr(ubg), self._ptr(x),
@@ -195,6 +217,61 @@ class BatchedCentroidalMPC:
         _check(self.lib.cmpc_solve_host(self.handle, B, vp(p), vp(lbg), vp(ubg), vp(x), vp(lam), vp(obj), vp(status),
                                         vp(iters), int(lam_g0 is not None)), "cmpc_solve_host", self.handle)
         return x, lam, obj, status, iters
+
+    def solve_ticks_host(self, ticks, warm_mode=0, x_prev=None, lam_prev=None, want_lam=True):
+        """numpy tick records in / numpy solution out through cmpc_solve_ticks_host (the per-tick call of a host controller):
+        uploads the records, populates (p, lbg, ubg, x0) on the device, solves, downloads.  warm_mode 1: warm start from the
+        solution the previous call left on the device; 2: from x_prev / lam_prev (unshifted)."""
+        ticks = np.ascontiguousarray(ticks, dtype=np.float64)
+        B = ticks.shape[0]
+        assert ticks.shape[1] == self.lib.cmpc_tick_stride(self.N)
+        x = np.zeros((B, self.L.n)) if x_prev is None else np.array(x_prev, dtype=np.float64, copy=True, order="C")
+        lam = None
+        if want_lam or lam_prev is not None:
+            lam = np.zeros((B, self.L.m)) if lam_prev is None else np.array(lam_prev, dtype=np.float64, copy=True, order="C")
+        obj, status, iters = np.zeros(B), np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.int32)
+        vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        _check(self.lib.cmpc_solve_ticks_host(self.handle, B, vp(ticks), int(warm_mode), vp(x), vp(lam), vp(obj), vp(status),
+                                              vp(iters)), "cmpc_solve_ticks_host", self.handle)
+        return x, lam, obj, status, iters
+
+    def populate(self, ticks, want_x0=True):
+        """tick records (device tensor) -> (p, lbg, ubg, x0) device tensors (cmpc_populate)"""
+        import torch
+        B = ticks.shape[0]
+        mk = lambda n: torch.empty(B, n, dtype=torch.float64, device=self.device)  # noqa: E731
+        p, lbg, ubg = mk(self.L.np), mk(self.L.m), mk(self.L.m)
+        x0 = mk(self.L.n) if want_x0 else None
+        self.populate_into(ticks, p, lbg, ubg, x0)
+        return p, lbg, ubg, x0
+
+    def populate_into(self, ticks, p, lbg, ubg, x0=None):
+        _check(self.lib.cmpc_populate(self.handle, ticks.shape[0], self._ptr(ticks), self._ptr(p), self._ptr(lbg), self._ptr(ubg),
+                                      self._ptr(x0), self._stream()), "cmpc_populate", self.handle)
+
+    def resample_references(self, ticks, t_in, com_in, h_in, t_out, robot_mass=1.0, com_height=-1.0):
+        _check(self.lib.cmpc_resample_references(self.handle, ticks.shape[0], t_in.shape[0], self._ptr(t_in), self._ptr(com_in),
+                                                 self._ptr(h_in), self._ptr(t_out), float(robot_mass), float(com_height),
+                                                 self._ptr(ticks), self._stream()), "cmpc_resample_references", self.handle)
+
+    def desired_zmp(self, x, p, half_length=0.08, half_width=0.03):
+        import torch
+        B = x.shape[0]
+        zmp = torch.empty(B, 2, dtype=torch.float64, device=self.device)
+        valid = torch.empty(B, dtype=torch.int32, device=self.device)
+        _check(self.lib.cmpc_desired_zmp(self.handle, B, self._ptr(x), self._ptr(p), float(half_length), float(half_width),
+                                         self._ptr(zmp), self._ptr(valid), self._stream()), "cmpc_desired_zmp", self.handle)
+        return zmp, valid
+
+    def rollout_tick(self, wp, tick, roll, state, steps, ticks, ext6, step_adjust=True):
+        _check(self.lib.cmpc_rollout_tick(self.handle, C.byref(wp), roll.shape[0], int(tick), self._ptr(roll), self._ptr(state),
+                                          self._ptr(steps), self._ptr(ticks), self._ptr(ext6), int(bool(step_adjust)), self._stream()),
+               "cmpc_rollout_tick", self.handle)
+
+    def rollout_feedback(self, wp, tick, x, p, state, status, iters, roll, steps):
+        _check(self.lib.cmpc_rollout_feedback(self.handle, C.byref(wp), roll.shape[0], int(tick), self._ptr(x), self._ptr(p),
+                                              self._ptr(state), self._ptr(status), self._ptr(iters), self._ptr(roll),
+                                              self._ptr(steps), self._stream()), "cmpc_rollout_feedback", self.handle)
 
     def shift_warmstart(self, x, lam_g=None):
         _check(self.lib.cmpc_shift_warmstart(self.handle, x.shape[0], self._ptr(x), self._ptr(lam_g), self._stream()),

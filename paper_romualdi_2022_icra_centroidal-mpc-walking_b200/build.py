@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libcmpc_b200.so")
 HOSTLIB = os.path.join(HERE, "libcmpc_host.so")
 SOURCES = [os.path.join(HERE, "csrc", "cmpc_kernels.cu")]
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("cmpc_kernels.cu", "cmpc_core.cuh", "cmpc_warp.cuh", "cmpc_ipm.cuh", "cmpc_layout.cuh", "cmpc_sparse.cuh")]
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("cmpc_kernels.cu", "cmpc_core.cuh", "cmpc_warp.cuh", "cmpc_ipm.cuh", "cmpc_layout.cuh", "cmpc_sparse.cuh", "cmpc_populate.cuh")]
 DEPS.append(os.path.join(os.path.dirname(HERE), "include", "cmpc_b200.h"))
 HOST_SOURCES = [os.path.join(HERE, "host", f) for f in ("CentroidalMPC.cpp", "IniParametersHandler.cpp", "Contacts.cpp", "BlockUtilities.cpp", "capi.cpp")]
 

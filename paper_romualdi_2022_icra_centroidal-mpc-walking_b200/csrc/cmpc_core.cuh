@@ -51,6 +51,7 @@ struct Config {
     double scal_max_grad;  // nlp_scaling_max_gradient (IPOPT default 100; 0: no scaling of the objective)
     double acc_tol;        // acceptable_tol (IPOPT default 1e-6; 0: no acceptable-level termination)
     int acc_iter;          // acceptable_iter (IPOPT default 15)
+    double box_lo[NC][3], box_up[NC][3];   // CONTACT_c bounding_box_lower_limit / upper_limit (step adjustment, contact frame)
 };
 
 struct Instance {  // CasADi order, read only

@@ -20,6 +20,7 @@
 #include "../../include/cmpc_b200.h"
 #include "cmpc_sparse.cuh"
 #include "cmpc_ipm.cuh"
+#include "cmpc_populate.cuh"
 
 namespace cmpc {
 
@@ -415,6 +416,8 @@ struct cmpc_handle_s {
     // staging buffers of cmpc_solve_host
     int host_cap = 0;
     double *d_p = nullptr, *d_lbg = nullptr, *d_ubg = nullptr, *d_x = nullptr, *d_lam = nullptr, *d_obj = nullptr;
+    double* d_ticks = nullptr;
+    int resident_batch = 0;  // batch size of the solution the last host call left in d_x / d_lam (warm_mode 1)
     int *d_status = nullptr, *d_iters = nullptr;
     long long launches = 0;
     int last_cuda = 0;
@@ -463,6 +466,9 @@ int cmpc_default_config(cmpc_config* c)
     c->mu_strategy = CMPC_MU_DEFAULT;
     c->warm_start_mu_init = 0.01;
     c->nlp_scaling_max_gradient = 100.0; c->acceptable_tol = 1e-6; c->acceptable_iter = 15;
+    const double up[2][3] = {{0.01, 0.05, 0.0}, {0.01, 0.0, 0.0}}, lo[2][3] = {{-0.01, 0.0, 0.0}, {-0.01, -0.05, 0.0}};
+    memcpy(c->bounding_box_upper_limit, up, sizeof up);
+    memcpy(c->bounding_box_lower_limit, lo, sizeof lo);
     return CMPC_OK;
 }
 
@@ -533,6 +539,8 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
     c.scal_max_grad = u->nlp_scaling_max_gradient == 0.0 ? 100.0 : (u->nlp_scaling_max_gradient > 0.0 ? u->nlp_scaling_max_gradient : 0.0);
     c.acc_tol = u->acceptable_tol == 0.0 ? 1e-6 : (u->acceptable_tol > 0.0 ? u->acceptable_tol : 0.0);
     c.acc_iter = u->acceptable_iter > 0 ? u->acceptable_iter : 15;
+    memcpy(c.box_lo, u->bounding_box_lower_limit, sizeof c.box_lo);
+    memcpy(c.box_up, u->bounding_box_upper_limit, sizeof c.box_up);
     h->device = u->device;
     DeviceGuard guard(h->device);
     cudaError_t e = guard.err;
@@ -613,7 +621,7 @@ int cmpc_destroy(cmpc_handle h)
         if (h->done) cudaEventDestroy(h->done);
         cudaFree(h->d_work); cudaFree(h->d_counter); cudaFree(h->d_jslot); cudaFree(h->d_hslot); cudaFree(h->d_gscratch); cudaFree(h->d_cmap);
         cudaFree(h->d_p); cudaFree(h->d_lbg); cudaFree(h->d_ubg); cudaFree(h->d_x); cudaFree(h->d_lam); cudaFree(h->d_obj);
-        cudaFree(h->d_status); cudaFree(h->d_iters);
+        cudaFree(h->d_status); cudaFree(h->d_iters); cudaFree(h->d_ticks);
     }
     delete h;
     return CMPC_OK;
@@ -627,8 +635,12 @@ int cmpc_solve_batched(cmpc_handle h, int batch, const double* d_p, const double
     if (batch == 0) return CMPC_OK;
     cudaStream_t st = (cudaStream_t)stream;
     CMPC_ON_DEVICE(h);
-    // one work queue and one scratch arena per handle: a solve on another stream than the previous one is ordered behind it
-    if (h->in_flight && st != h->last_stream) CK(cudaStreamWaitEvent(st, h->done, 0));
+    // one work queue and one scratch arena per handle: a solve on another stream than the previous one is ordered behind it.
+    // While the stream is being captured into a CUDA graph the event is left alone: a graph replays in stream order.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CK(cudaStreamIsCapturing(st, &cap));
+    const bool capturing = cap != cudaStreamCaptureStatusNone;
+    if (!capturing && h->in_flight && st != h->last_stream) CK(cudaStreamWaitEvent(st, h->done, 0));
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
     // small batches are latency bound: independent single-team CTAs of 128 threads (no lock-step, no 80-register cap) beat the
     // seven-team CTAs while at most four of them share an SM (profiles/r1_notes.md): up to 2 per SM the kernel compiled
@@ -655,9 +667,11 @@ int cmpc_solve_batched(cmpc_handle h, int batch, const double* d_p, const double
     }
     h->launches++;
     CK(cudaGetLastError());
-    CK(cudaEventRecord(h->done, st));
-    h->last_stream = st;
-    h->in_flight = true;
+    if (!capturing) {
+        CK(cudaEventRecord(h->done, st));
+        h->last_stream = st;
+        h->in_flight = true;
+    }
     return CMPC_OK;
 }
 
@@ -667,18 +681,20 @@ static int ensure_host_staging(cmpc_handle h, int batch)
     const int N = h->cfg.N;
     if (h->in_flight) cudaEventSynchronize(h->done);  // a solve in flight may still read the old buffers
     cudaFree(h->d_p); cudaFree(h->d_lbg); cudaFree(h->d_ubg); cudaFree(h->d_x); cudaFree(h->d_lam); cudaFree(h->d_obj);
-    cudaFree(h->d_status); cudaFree(h->d_iters);
-    h->d_p = h->d_lbg = h->d_ubg = h->d_x = h->d_lam = h->d_obj = nullptr;
+    cudaFree(h->d_status); cudaFree(h->d_iters); cudaFree(h->d_ticks);
+    h->d_p = h->d_lbg = h->d_ubg = h->d_x = h->d_lam = h->d_obj = h->d_ticks = nullptr;
     h->d_status = h->d_iters = nullptr;
     h->host_cap = 0;
+    h->resident_batch = 0;
     size_t b = (size_t)batch;
     if (cudaMalloc(&h->d_p, 8 * b * dim_p(N)) != cudaSuccess || cudaMalloc(&h->d_lbg, 8 * b * dim_g(N)) != cudaSuccess ||
         cudaMalloc(&h->d_ubg, 8 * b * dim_g(N)) != cudaSuccess || cudaMalloc(&h->d_x, 8 * b * dim_x(N)) != cudaSuccess ||
         cudaMalloc(&h->d_lam, 8 * b * dim_g(N)) != cudaSuccess || cudaMalloc(&h->d_obj, 8 * b) != cudaSuccess ||
-        cudaMalloc(&h->d_status, 4 * b) != cudaSuccess || cudaMalloc(&h->d_iters, 4 * b) != cudaSuccess) {
+        cudaMalloc(&h->d_status, 4 * b) != cudaSuccess || cudaMalloc(&h->d_iters, 4 * b) != cudaSuccess ||
+        cudaMalloc(&h->d_ticks, 8 * b * tick_stride(N)) != cudaSuccess) {
         cudaFree(h->d_p); cudaFree(h->d_lbg); cudaFree(h->d_ubg); cudaFree(h->d_x); cudaFree(h->d_lam); cudaFree(h->d_obj);
-        cudaFree(h->d_status); cudaFree(h->d_iters);
-        h->d_p = h->d_lbg = h->d_ubg = h->d_x = h->d_lam = h->d_obj = nullptr;
+        cudaFree(h->d_status); cudaFree(h->d_iters); cudaFree(h->d_ticks);
+        h->d_p = h->d_lbg = h->d_ubg = h->d_x = h->d_lam = h->d_obj = h->d_ticks = nullptr;
         h->d_status = h->d_iters = nullptr;
         return CMPC_E_ALLOC;
     }
@@ -710,6 +726,138 @@ int cmpc_solve_host(cmpc_handle h, int batch, const double* p, const double* lbg
     if (status) CK(cudaMemcpyAsync(status, h->d_status, 4 * b, cudaMemcpyDeviceToHost, 0));
     if (iters) CK(cudaMemcpyAsync(iters, h->d_iters, 4 * b, cudaMemcpyDeviceToHost, 0));
     CK(cudaStreamSynchronize(0));
+    h->resident_batch = batch;
+    return CMPC_OK;
+}
+
+int cmpc_tick_stride(int horizon) { return horizon < 1 ? CMPC_E_INVALID : tick_stride(horizon); }
+
+int cmpc_populate(cmpc_handle h, int batch, const double* d_ticks, double* d_p, double* d_lbg, double* d_ubg, double* d_x0,
+                  void* stream)
+{
+    if (!h || batch < 0 || !d_ticks || !d_p || !d_lbg || !d_ubg) return CMPC_E_INVALID;
+    if (batch == 0) return CMPC_OK;
+    CMPC_ON_DEVICE(h);
+    const int grid = std::min(batch, h->sm_count * 8);
+    cmpc_populate_kernel<<<grid, 64, sizeof(double) * tick_stride(h->cfg.N), (cudaStream_t)stream>>>(h->cfg, batch, d_ticks, d_p, d_lbg,
+                                                                                                    d_ubg, d_x0);
+    h->launches++;
+    CK(cudaGetLastError());
+    return CMPC_OK;
+}
+
+int cmpc_solve_ticks_host(cmpc_handle h, int batch, const double* ticks, int warm_mode, double* x, double* lam_g, double* obj,
+                          int* status, int* iters)
+{
+    if (!h || batch < 0 || !ticks || !x || warm_mode < 0 || warm_mode > 2) return CMPC_E_INVALID;
+    if (batch == 0) return CMPC_OK;
+    if (warm_mode == 1 && h->resident_batch != batch) return CMPC_E_INVALID;   // nothing (or something else) is resident
+    CMPC_ON_DEVICE(h);
+    int rc = ensure_host_staging(h, batch);
+    if (rc) return rc;
+    const int N = h->cfg.N;
+    const size_t b = (size_t)batch;
+    CK(cudaMemcpyAsync(h->d_ticks, ticks, 8 * b * tick_stride(N), cudaMemcpyHostToDevice, 0));
+    bool warm_duals = false;
+    if (warm_mode == 2) {
+        CK(cudaMemcpyAsync(h->d_x, x, 8 * b * dim_x(N), cudaMemcpyHostToDevice, 0));
+        if (lam_g) CK(cudaMemcpyAsync(h->d_lam, lam_g, 8 * b * dim_g(N), cudaMemcpyHostToDevice, 0));
+        warm_duals = lam_g != nullptr;
+    } else if (warm_mode == 1) warm_duals = true;
+    rc = cmpc_populate(h, batch, h->d_ticks, h->d_p, h->d_lbg, h->d_ubg, warm_mode == 0 ? h->d_x : nullptr, nullptr);
+    if (rc) return rc;
+    if (warm_mode != 0) {
+        rc = cmpc_shift_warmstart(h, batch, h->d_x, warm_duals ? h->d_lam : nullptr, nullptr);
+        if (rc) return rc;
+    }
+    rc = cmpc_solve_batched(h, batch, h->d_p, h->d_lbg, h->d_ubg, h->d_x, h->d_lam, h->d_obj, h->d_status, h->d_iters,
+                            warm_duals ? 1 : 0, nullptr);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(x, h->d_x, 8 * b * dim_x(N), cudaMemcpyDeviceToHost, 0));
+    if (lam_g) CK(cudaMemcpyAsync(lam_g, h->d_lam, 8 * b * dim_g(N), cudaMemcpyDeviceToHost, 0));
+    if (obj) CK(cudaMemcpyAsync(obj, h->d_obj, 8 * b, cudaMemcpyDeviceToHost, 0));
+    if (status) CK(cudaMemcpyAsync(status, h->d_status, 4 * b, cudaMemcpyDeviceToHost, 0));
+    if (iters) CK(cudaMemcpyAsync(iters, h->d_iters, 4 * b, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    h->resident_batch = batch;
+    return CMPC_OK;
+}
+
+int cmpc_resample_references(cmpc_handle h, int batch, int n_in, const double* d_t_in, const double* d_com_in,
+                             const double* d_h_in, const double* d_t_out, double robot_mass, double com_height, double* d_ticks,
+                             void* stream)
+{
+    if (!h || batch < 0 || n_in < 1 || !d_t_in || !d_com_in || !d_h_in || !d_t_out || !d_ticks || !(robot_mass > 0)) return CMPC_E_INVALID;
+    if (batch == 0) return CMPC_OK;
+    CMPC_ON_DEVICE(h);
+    const int N = h->cfg.N;
+    const long long total = (long long)batch * (N + 1);
+    const int grid = (int)std::min<long long>((total + 127) / 128, (long long)h->sm_count * 8);
+    cmpc_resample_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(N, batch, n_in, d_t_in, d_com_in, d_h_in, d_t_out, 1.0 / robot_mass,
+                                                                 com_height, d_ticks);
+    h->launches++;
+    CK(cudaGetLastError());
+    return CMPC_OK;
+}
+
+int cmpc_desired_zmp(cmpc_handle h, int batch, const double* d_x, const double* d_p, double half_length, double half_width,
+                     double* d_zmp, int* d_valid, void* stream)
+{
+    if (!h || batch < 0 || !d_x || !d_p || !d_zmp) return CMPC_E_INVALID;
+    if (batch == 0) return CMPC_OK;
+    CMPC_ON_DEVICE(h);
+    const int grid = std::min((batch + 127) / 128, h->sm_count * 8);
+    cmpc_zmp_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(h->cfg, batch, d_x, d_p, half_length, half_width, d_zmp, d_valid);
+    h->launches++;
+    CK(cudaGetLastError());
+    return CMPC_OK;
+}
+
+int cmpc_rollout_layout(int* roll_stride, int* max_steps, int* step_stride)
+{
+    if (roll_stride) *roll_stride = ROLL_STRIDE;
+    if (max_steps) *max_steps = RL_MAXSTEPS;
+    if (step_stride) *step_stride = RL_STEP;
+    return CMPC_OK;
+}
+
+static bool walk_params(const cmpc_walk_params* w, WalkParams& W)
+{
+    if (!w || w->ds_knots < 0 || w->ss_knots < 1) return false;
+    W.ds = w->ds_knots; W.ss = w->ss_knots; W.step_length = w->step_length; W.com_height = w->com_height;
+    W.push_threshold = w->push_threshold; W.zmp_half_length = w->zmp_half_length; W.zmp_half_width = w->zmp_half_width;
+    return true;
+}
+
+int cmpc_rollout_tick(cmpc_handle h, const cmpc_walk_params* w, int batch, int tick, const double* d_roll, const double* d_state,
+                      const double* d_steps, double* d_ticks, double* d_ext6, int step_adjust, void* stream)
+{
+    WalkParams W;
+    if (!h || batch < 0 || !d_roll || !d_state || !d_steps || !d_ticks || !d_ext6 || !walk_params(w, W)) return CMPC_E_INVALID;
+    if (batch == 0) return CMPC_OK;
+    CMPC_ON_DEVICE(h);
+    const int grid = std::min((batch + 63) / 64, h->sm_count * 8);
+    cmpc_rollout_tick_kernel<<<grid, 64, 0, (cudaStream_t)stream>>>(h->cfg, W, batch, tick, d_roll, d_state, d_steps, d_ticks, d_ext6,
+                                                                    step_adjust);
+    h->launches++;
+    CK(cudaGetLastError());
+    return CMPC_OK;
+}
+
+int cmpc_rollout_feedback(cmpc_handle h, const cmpc_walk_params* w, int batch, int tick, const double* d_x, const double* d_p,
+                          const double* d_state, const int* d_status, const int* d_iters, double* d_roll, double* d_steps,
+                          void* stream)
+{
+    WalkParams W;
+    if (!h || batch < 0 || !d_x || !d_p || !d_state || !d_status || !d_iters || !d_roll || !d_steps || !walk_params(w, W))
+        return CMPC_E_INVALID;
+    if (batch == 0) return CMPC_OK;
+    CMPC_ON_DEVICE(h);
+    const int grid = std::min((batch + 63) / 64, h->sm_count * 8);
+    cmpc_rollout_feedback_kernel<<<grid, 64, 0, (cudaStream_t)stream>>>(h->cfg, W, batch, tick, d_x, d_p, d_state, d_status, d_iters,
+                                                                        d_roll, d_steps);
+    h->launches++;
+    CK(cudaGetLastError());
     return CMPC_OK;
 }
 

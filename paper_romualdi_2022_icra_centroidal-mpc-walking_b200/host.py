@@ -42,6 +42,7 @@ def load_host_library() -> C.CDLL:
     L.cmpch_set_contact_list.argtypes = [vp, s, i, _dp, _dp, _dp, _dp]
     L.cmpch_commit_contacts.argtypes = [vp, d]
     L.cmpch_get_inputs.argtypes = [vp, _dp, _dp, _dp, _dp]
+    L.cmpch_get_tick.argtypes = [vp, _dp]
     L.cmpch_advance.argtypes = [vp]
     L.cmpch_advance_batch.argtypes = [C.POINTER(vp), i]
     L.cmpch_is_output_valid.argtypes = [vp]
@@ -134,6 +135,13 @@ class CentroidalMPCHost:
         if self.lib.cmpch_get_inputs(self.h, _p(p), _p(lbg), _p(ubg), _p(x0)) != 0:
             raise RuntimeError(self.last_error())
         return p, lbg, ubg, x0
+
+    def tick_record(self):
+        """the compact tick record advance() uploads (include/cmpc_b200.h): 6 N + 194 doubles"""
+        t = np.zeros(6 * self.N + 194)
+        if self.lib.cmpch_get_tick(self.h, _p(t)) != 0:
+            raise RuntimeError(self.last_error())
+        return t
 
     def advance(self) -> bool:
         return self.lib.cmpch_advance(self.h) == 0

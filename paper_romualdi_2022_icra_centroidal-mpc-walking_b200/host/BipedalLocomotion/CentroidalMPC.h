@@ -64,6 +64,9 @@ public:
     // the solver's formal input for the current tick in the reference's CasADi order: p[50N+27],
     // lbg/ubg[53N+15], x0[45N+15].  Host-only (no GPU needed): what advance() would hand to the solver.
     bool getSolverInputs(std::vector<double>& p, std::vector<double>& lbg, std::vector<double>& ubg, std::vector<double>& x0) const;
+    // the compact tick record advance() uploads for the current tick (cmpc_tick_stride(horizon) doubles, include/cmpc_b200.h):
+    // state, wrench, references and the contact windows; the device expands it into the formal input.  Host-only.
+    bool getTickRecord(double* tick) const;
     const CentroidalMPCSolverStats& getSolverStats() const;
     bool getConfig(cmpc_config& cfg) const;
     int horizon() const;

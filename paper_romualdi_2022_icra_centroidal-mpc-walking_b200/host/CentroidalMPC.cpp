@@ -109,6 +109,13 @@ struct CentroidalMPC::Impl {
     bool loadParameters(const ParametersHandler::IParametersHandler& h);
     bool fillInputs(std::vector<double>& p_, std::vector<double>& lbg_, std::vector<double>& ubg_, std::vector<double>& x0_,
                     std::vector<double>* lam0_) const;
+    // the compact tick record of include/cmpc_b200.h (what advance() uploads; the device expands it: cmpc_populate)
+    bool fillTick(double* tick);
+    // knot-wise contact activity and the knot-0 rotations of the tick in flight (unpack needs them; p stays on the device)
+    std::vector<char> enabled[NC];
+    Eigen::Matrix3d rot0[NC];
+    // controllers whose previous solutions are resident on the device of THIS controller's handle, in batch order
+    std::vector<const CentroidalMPC*> residentBatch;
     bool ensureHandle();
     void unpack(std::chrono::nanoseconds elapsed);
 };
@@ -201,7 +208,11 @@ bool CentroidalMPC::Impl::loadParameters(const ParametersHandler::IParametersHan
     }
     std::sort(contacts.begin(), contacts.end(), [](const ContactConfig& a, const ContactConfig& b) { return a.name < b.name; });
     if (contacts[0].name == contacts[1].name) return fail("the two contacts must have different names");
-    for (int c = 0; c < NC; ++c) std::memcpy(cfg.corners[c], contacts[c].corners, sizeof(double) * NJ * 3);
+    for (int c = 0; c < NC; ++c) {
+        std::memcpy(cfg.corners[c], contacts[c].corners, sizeof(double) * NJ * 3);
+        std::memcpy(cfg.bounding_box_upper_limit[c], contacts[c].boxUpper, sizeof(double) * 3);
+        std::memcpy(cfg.bounding_box_lower_limit[c], contacts[c].boxLower, sizeof(double) * 3);
+    }
     return true;
 }
 
@@ -321,6 +332,59 @@ bool CentroidalMPC::Impl::fillInputs(std::vector<double>& p_, std::vector<double
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------------- tick record
+bool CentroidalMPC::Impl::fillTick(double* tick)
+{
+    const int N = L.N;
+    const int stride = cmpc_tick_stride(N);
+    std::fill(tick, tick + stride, 0.0);
+    for (int a = 0; a < 3; ++a) {
+        tick[a] = com[a]; tick[3 + a] = dcom[a]; tick[6 + a] = angMom[a];
+        tick[9 + a] = wrench.force()[a]; tick[12 + a] = wrench.torque()[a];
+    }
+    tick[15] = stepAdjustmentEnabled ? 1.0 : 0.0;
+    for (int k = 0; k <= N; ++k) {
+        std::memcpy(tick + 17 + 3 * k, comRef[k].data(), 24);
+        std::memcpy(tick + 17 + 3 * (N + 1) + 3 * k, angMomRef[k].data(), 24);
+    }
+    const auto t0 = currentTime;
+    const auto horizonEnd = t0 + N * dT;
+    constexpr int kMaxContacts = 6, kRecord = 14;
+    for (int c = 0; c < NC; ++c) {
+        const auto lit = phaseList.lists().find(contacts[c].name);
+        if (lit == phaseList.lists().end()) return false;
+        const ContactList& list = lit->second;
+        // window: from the contact the foot stands (or last stood) on -- one earlier if that one was still active a sampling
+        // time ago -- up to the first contact that starts after the horizon
+        auto start = list.getPresentContact(t0);
+        if (start == list.cend()) start = list.cbegin();
+        else if (start != list.cbegin()) {
+            auto prev = start; --prev;
+            if (prev->isContactActive(t0 - dT)) start = prev;
+        }
+        double* out = tick + 17 + 6 * (N + 1) + c * (1 + kMaxContacts * kRecord);
+        int n = 0;
+        for (auto it = start; it != list.cend(); ++it) {
+            if (n == kMaxContacts) return fail("more than 6 contacts of " + contacts[c].name + " inside the horizon");
+            double* r = out + 1 + n * kRecord;
+            const auto relOn = it->activationTime - t0;
+            r[0] = (double)relOn.count();
+            r[1] = it->deactivationTime == std::chrono::nanoseconds::max() ? 1e18 : (double)(it->deactivationTime - t0).count();
+            std::memcpy(r + 2, it->pose.translation().data(), 24);
+            std::memcpy(r + 5, it->pose.rotation().data(), 72);
+            ++n;
+            if (it->activationTime > horizonEnd) break;
+        }
+        out[0] = (double)n;
+        // what unpack() needs of the formal input
+        enabled[c].assign(N, 0);
+        for (int k = 0; k < N; ++k) enabled[c][k] = list.getActiveContact(t0 + k * dT) != list.cend() ? 1 : 0;
+        const auto a0 = list.getActiveContact(t0);
+        rot0[c] = a0 != list.cend() ? a0->pose.rotation() : Eigen::Matrix3d::Identity();
+    }
+    return true;
+}
+
 bool CentroidalMPC::Impl::ensureHandle()
 {
     if (handle) return true;
@@ -351,10 +415,8 @@ void CentroidalMPC::Impl::unpack(std::chrono::nanoseconds elapsed)
         dc.index = c;
         Eigen::Vector3d pos;
         std::memcpy(pos.data(), &x[L.x_pos(c, 0)], 24);
-        Eigen::Matrix3d R;
-        std::memcpy(R.m, &p[L.p_rot(c, 0)], 72);
-        dc.pose = manif::SE3d(pos, R);
-        const double en0 = p[L.p_en(c, 0)];
+        dc.pose = manif::SE3d(pos, rot0[c]);
+        const double en0 = enabled[c][0] ? 1.0 : 0.0;
         dc.corners.resize(NJ);
         for (int j = 0; j < NJ; ++j) {
             dc.corners[j].position = Eigen::Vector3d(contacts[c].corners[j][0], contacts[c].corners[j][1], contacts[c].corners[j][2]);
@@ -365,7 +427,7 @@ void CentroidalMPC::Impl::unpack(std::chrono::nanoseconds elapsed)
         ContactList& list = lists[dc.name];
         int landing = -1;
         for (int k = 1; k < N; ++k)
-            if (p[L.p_en(c, k)] > 0.5 && p[L.p_en(c, k - 1)] < 0.5) { landing = k; break; }
+            if (enabled[c][k] && !enabled[c][k - 1]) { landing = k; break; }
         if (landing > 0) {
             const auto it = list.getActiveContact(currentTime + landing * dT);
             if (it != list.cend()) {
@@ -448,6 +510,14 @@ bool CentroidalMPC::getSolverInputs(std::vector<double>& p, std::vector<double>&
     return true;
 }
 
+bool CentroidalMPC::getTickRecord(double* tick) const
+{
+    if (m_pimpl->fsm == State::NotInitialized || !m_pimpl->hasState || !m_pimpl->hasReference || !m_pimpl->hasContacts)
+        return m_pimpl->fail("getTickRecord: state, reference trajectory and contact phase list must be set");
+    if (!m_pimpl->fillTick(tick)) return m_pimpl->fail("getTickRecord: inconsistent contact phase list");
+    return true;
+}
+
 bool CentroidalMPC::advance() { return advanceBatch({this}); }
 
 bool CentroidalMPC::advanceBatch(const std::vector<CentroidalMPC*>& controllers)
@@ -467,30 +537,44 @@ bool CentroidalMPC::advanceBatch(const std::vector<CentroidalMPC*>& controllers)
     }
     if (!first.ensureHandle()) return false;
     const auto tic = std::chrono::steady_clock::now();
-    std::vector<double> P(B * L.np()), LB(B * L.m()), UB(B * L.m()), X(B * L.n()), LAM(B * L.m());
-    bool warm = true;
+    // The host ships one compact tick record per controller (state, references, contact windows); the formal input
+    // (p, lbg, ubg, x0) is expanded on the device (cmpc_populate) and the solution stays resident there for the warm start
+    // of the next tick: per tick and controller 2.3 KB go up and x (plus lam_g with the warm start on) comes back.
+    const int stride = cmpc_tick_stride(L.N);
+    std::vector<double> T(B * stride), X(B * L.n());
+    bool warm = true, wantLam = false;
     for (size_t b = 0; b < B; ++b) {
         Impl& I = *controllers[b]->m_pimpl;
-        std::vector<double> lam0;
-        if (!I.fillInputs(I.p, I.lbg, I.ubg, I.x, &lam0)) return I.fail("advance: inconsistent contact phase list");
+        if (!I.fillTick(T.data() + b * stride)) return I.fail("advance: inconsistent contact phase list");
         warm = warm && I.warmStartEnabled && I.hasPrevious;
-        std::copy(I.p.begin(), I.p.end(), P.begin() + b * L.np());
-        std::copy(I.lbg.begin(), I.lbg.end(), LB.begin() + b * L.m());
-        std::copy(I.ubg.begin(), I.ubg.end(), UB.begin() + b * L.m());
-        std::copy(I.x.begin(), I.x.end(), X.begin() + b * L.n());
-        std::copy(lam0.begin(), lam0.end(), LAM.begin() + b * L.m());
+        wantLam = wantLam || I.warmStartEnabled;
+    }
+    std::vector<const CentroidalMPC*> batch(controllers.begin(), controllers.end());
+    int warmMode = 0;
+    std::vector<double> LAM;
+    if (wantLam) LAM.assign(B * L.m(), 0.0);
+    if (warm) {
+        if (first.residentBatch == batch) warmMode = 1;   // the previous solutions of exactly this batch are on the device
+        else {
+            warmMode = 2;   // upload them: the device shifts them by one knot (cmpc_shift_warmstart)
+            for (size_t b = 0; b < B; ++b) {
+                Impl& I = *controllers[b]->m_pimpl;
+                std::copy(I.xPrev.begin(), I.xPrev.end(), X.begin() + b * L.n());
+                std::copy(I.lamPrev.begin(), I.lamPrev.end(), LAM.begin() + b * L.m());
+            }
+        }
     }
     std::vector<double> obj(B);
     std::vector<int> status(B), iters(B);
-    const int rc = cmpc_solve_host(first.handle, (int)B, P.data(), LB.data(), UB.data(), X.data(), LAM.data(), obj.data(),
-                                   status.data(), iters.data(), warm ? 1 : 0);
-    if (rc != CMPC_OK) return first.fail(std::string("cmpc_solve_host failed: ") + cmpc_error_string(rc));
+    const int rc = cmpc_solve_ticks_host(first.handle, (int)B, T.data(), warmMode, X.data(), wantLam ? LAM.data() : nullptr,
+                                         obj.data(), status.data(), iters.data());
+    if (rc != CMPC_OK) { first.residentBatch.clear(); return first.fail(std::string("cmpc_solve_ticks_host failed: ") + cmpc_error_string(rc)); }
     const auto elapsed = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - tic);
     bool ok = true;
     for (size_t b = 0; b < B; ++b) {
         Impl& I = *controllers[b]->m_pimpl;
         I.x.assign(X.begin() + b * L.n(), X.begin() + (b + 1) * L.n());
-        I.lam.assign(LAM.begin() + b * L.m(), LAM.begin() + (b + 1) * L.m());
+        if (wantLam) I.lam.assign(LAM.begin() + b * L.m(), LAM.begin() + (b + 1) * L.m());
         I.stats.status = status[b]; I.stats.iterations = iters[b]; I.stats.objective = obj[b];
         // IPOPT failure => CasADi throws => BLF returns false; "Solved To Acceptable Level" counts as success for CasADi
         if (status[b] != CMPC_STATUS_CONVERGED && status[b] != CMPC_STATUS_ACCEPTABLE) {
@@ -503,6 +587,8 @@ bool CentroidalMPC::advanceBatch(const std::vector<CentroidalMPC*>& controllers)
         I.currentTime += I.dT;  // the controller keeps its own clock: one sampling time per advance()
         I.fsm = State::OutputValid;
     }
+    // a failed instance keeps its older previous solution on the host: what is resident no longer matches
+    if (ok) first.residentBatch = batch; else first.residentBatch.clear();
     return ok;
 }
 

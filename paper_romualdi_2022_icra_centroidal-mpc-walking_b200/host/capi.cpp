@@ -89,6 +89,8 @@ int cmpch_get_inputs(void* v, double* p, double* lbg, double* ubg, double* x0)
     std::memcpy(ubg, UB.data(), 8 * UB.size()); std::memcpy(x0, X.data(), 8 * X.size());
     return 0;
 }
+// the compact tick record advance() would upload (cmpc_tick_stride(horizon) doubles)
+int cmpch_get_tick(void* v, double* tick) { return static_cast<Host*>(v)->mpc.getTickRecord(tick) ? 0 : -1; }
 int cmpch_advance(void* v) { return static_cast<Host*>(v)->mpc.advance() ? 0 : -1; }
 int cmpch_advance_batch(void** hosts, int n)
 {

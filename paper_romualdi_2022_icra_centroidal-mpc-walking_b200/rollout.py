@@ -65,6 +65,101 @@ class WalkSchedule:
         return out
 
 
+def rollout_tables(B: int, ticks: int, seed: int, N: int, dT: float, push_prob=1.0, push_range=(1.0, 3.0), yaw_range=0.0,
+                   step_length=0.1, foot_y=0.08, ds_time=0.3, ss_time=0.5):
+    """Host-side set-up of a batch of rollouts (numpy, seeded): the rollout records (phase of tick 0, push schedule), the
+    footstep tables of the synthetic planner and the initial plant states.  Layouts: cmpc_rollout_layout (include/cmpc_b200.h)."""
+    from . import load_library
+    import ctypes as C
+    rs, ms, ss_ = C.c_int(), C.c_int(), C.c_int()
+    load_library().cmpc_rollout_layout(C.byref(rs), C.byref(ms), C.byref(ss_))
+    RS, MAXS, ST = rs.value, ms.value, ss_.value
+    rng = np.random.default_rng(seed)
+    phase0 = rng.integers(0, 16, size=B)
+    push_tick = np.where(rng.uniform(size=B) < push_prob, rng.integers(5, max(6, ticks - 5), size=B), -1)
+    push_len = rng.integers(1, 3, size=B)                       # 0.1 - 0.2 s
+    ang = rng.uniform(0, 2 * np.pi, size=B)
+    mag = rng.uniform(*push_range, size=B)
+    roll = np.zeros((B, RS))
+    roll[:, 0] = phase0
+    roll[:, 1], roll[:, 2] = push_tick, push_len
+    roll[:, 3], roll[:, 4] = mag * np.cos(ang), mag * np.sin(ang)
+    roll[:, 9] = np.inf                                         # running minimum of the CoM height
+    roll[:, 10] = -np.inf                                       # running maximum of the ZMP excess
+    idx = np.arange(MAXS)
+    steps = np.zeros((B, 2, MAXS, ST))
+    steps[:, 0, :, 0] = 2 * step_length * idx
+    steps[:, 1, :, 0] = np.where(idx == 0, 0.0, step_length * (2 * idx - 1))
+    steps[:, 0, :, 1], steps[:, 1, :, 1] = foot_y, -foot_y
+    if yaw_range > 0:
+        steps[:, :, :, 3] = rng.uniform(-yaw_range, yaw_range, size=(B, 2, MAXS))
+    w0 = walk_batch(N=N, dT=dT, B=B, phase=phase0, step_length=step_length, foot_y=foot_y, ds_time=ds_time, ss_time=ss_time)
+    g0 = Layout(N).p_glob()
+    state = w0["p"][:, g0:g0 + 9].copy()
+    assert int(phase0.max()) + ticks + N < 16 * (MAXS - 2), "the footstep table is too short for this rollout"
+    return roll, steps, state
+
+
+def closed_loop_rollout_device(solver: BatchedCentroidalMPC, B: int, ticks: int, seed: int = 0, dT: float = 0.1, wbc_dt: float = 0.002,
+                               push_prob: float = 1.0, push_range=(1.0, 3.0), step_adjust: bool = True, yaw_range: float = 0.0,
+                               time_device: bool = False, use_graph: bool = True, ds_time=0.3, ss_time=0.5, step_length=0.1):
+    """The closed loop with every per-tick step on the device: cmpc_rollout_tick (planner + updateContactPhaseList + state
+    feedback -> tick records), cmpc_populate (records -> p, lbg, ubg), cmpc_shift_warmstart, cmpc_solve_batched,
+    cmpc_rollout_plant, cmpc_rollout_feedback (statistics, landed footsteps).  Six kernels per tick, no torch op and no host
+    synchronisation inside the loop; ticks 1 .. T - 1 are ONE captured CUDA graph replayed T - 1 times (use_graph).  Footstep
+    yaw is part of the footstep tables.  Returns the same statistics as closed_loop_rollout plus zmp_excess_max."""
+    from . import WalkParams
+    N, dev = solver.N, solver.device
+    L = Layout(N)
+    roll_h, steps_h, state_h = rollout_tables(B, ticks, seed, N, dT, push_prob, push_range, yaw_range, step_length=step_length,
+                                              ds_time=ds_time, ss_time=ss_time)
+    tens = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    roll, steps, state = tens(roll_h), tens(steps_h), tens(state_h)
+    wp = WalkParams(int(round(ds_time / dT)), int(round(ss_time / dT)), step_length, 0.7, PUSH_THRESHOLD, 0.08, 0.03)
+    mk = lambda n, dt=torch.float64: torch.zeros(B, n, dtype=dt, device=dev)  # noqa: E731
+    tk = mk(solver.lib.cmpc_tick_stride(N))
+    p, lbg, ubg, d_x, d_lam, ext6 = mk(L.np), mk(L.m), mk(L.m), mk(L.n), mk(L.m), mk(6)
+    out = (torch.zeros(B, dtype=torch.float64, device=dev), torch.zeros(B, dtype=torch.int32, device=dev),
+           torch.zeros(B, dtype=torch.int32, device=dev))
+    substeps = int(round(dT / wbc_dt))
+
+    def tick(first: bool):
+        solver.rollout_tick(wp, 0 if first else -1, roll, state, steps, tk, ext6, step_adjust)
+        solver.populate_into(tk, p, lbg, ubg, d_x if first else None)
+        if not first:
+            solver.shift_warmstart(d_x, d_lam)
+        solver.solve(p, lbg, ubg, d_x, d_lam, warm_duals=not first, out=out)
+        solver.rollout_plant(d_x, p, state, wbc_dt, substeps, ext=ext6)
+        solver.rollout_feedback(wp, 0 if first else -1, d_x, p, state, out[1], out[2], roll, steps)
+
+    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    stream = torch.cuda.Stream(device=dev) if use_graph else torch.cuda.current_stream(dev)
+    stream.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(stream):
+        ev[0].record()
+        tick(True)
+        if ticks > 1:
+            if use_graph:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=stream):
+                    tick(False)
+                # capturing does not execute: the captured tick is launched T - 1 times
+                for _ in range(ticks - 1):
+                    graph.replay()
+            else:
+                for _ in range(ticks - 1):
+                    tick(False)
+        ev[1].record()
+    torch.cuda.current_stream(dev).wait_stream(stream)
+    r = roll.cpu().numpy()
+    res = dict(converged_ticks=r[:, 6].astype(np.int64), iterations=r[:, 7].astype(np.int64), com_err_max=r[:, 8], com_z_min=r[:, 9],
+               zmp_excess_max=r[:, 10], push_tick=roll_h[:, 1].astype(np.int64), ticks=ticks, footsteps=steps.cpu().numpy())
+    if time_device:
+        torch.cuda.synchronize()
+        res["device_ms"] = float(ev[0].elapsed_time(ev[1]))
+    return res
+
+
 def closed_loop_rollout(solver: BatchedCentroidalMPC, B: int, ticks: int, seed: int = 0, dT: float = 0.1, wbc_dt: float = 0.002,
                         push_prob: float = 1.0, push_range=(1.0, 3.0), step_adjust: bool = True, yaw_range: float = 0.0,
                         time_device: bool = False, host_schedule: bool = False):

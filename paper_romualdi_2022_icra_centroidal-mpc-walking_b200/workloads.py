@@ -30,7 +30,7 @@ def _rotz(yaw):
 
 
 def walk_batch(N=12, dT=0.1, B=1, seed=0, phase=None, yaw_range=0.0, state_noise=0.0, step_adjust=True,
-               step_length=0.1, foot_y=0.08, com_height=0.7, ds_time=0.3, ss_time=0.5, push=None):
+               step_length=0.1, foot_y=0.08, com_height=0.7, ds_time=0.3, ss_time=0.5, push=None, ticks=False):
     """Batch of B MPC instances on the walk schedule.  Returns dict(p, lbg, ubg, x0) of float64 arrays.
 
     phase:       None -> random phase offset in [0, period) knots per instance (seeded); int -> that offset for all.
@@ -38,6 +38,7 @@ def walk_batch(N=12, dT=0.1, B=1, seed=0, phase=None, yaw_range=0.0, state_noise
     state_noise: scale s of com0 += U(-.03,.03)^3 s, dcom0 += U(-.2,.2)^3 s, h0 += U(-.05,.05)^3 s.
     step_adjust: False -> every step box is zero width (lower = upper = 0): footsteps cannot move.
     push:        optional (B,3) external force per unit mass applied at knot 0 (setState puts the wrench in column 0).
+    ticks:       True -> also "ticks": the same instances as compact tick records (state, references, contact windows).
     """
     L = Layout(N)
     rng = np.random.default_rng(seed)
@@ -144,7 +145,47 @@ def walk_batch(N=12, dT=0.1, B=1, seed=0, phase=None, yaw_range=0.0, state_noise
     # knots whose nominal position refers to the contact the foot stands on at knot 0 (incl. the lift-off knot), and the
     # stance flag at knot 0: what a closed loop needs to replace planned by actual footsteps (rollout.py)
     same = np.stack([(step[c] == step[c][:, :1]) & ~swing[c][:, :1] for c in range(NC)])
-    return dict(p=p, lbg=lbg, ubg=ubg, x0=x0, N=N, dT=dT, phase=ph, same_contact=same, stance0=~swing[:, :, 0], comref=comref)
+    out = dict(p=p, lbg=lbg, ubg=ubg, x0=x0, N=N, dT=dT, phase=ph, same_contact=same, stance0=~swing[:, :, 0], comref=comref)
+    if ticks:
+        # the same instances as TICK RECORDS (include/cmpc_b200.h): state, wrench, references and the contact windows of the walk
+        # as contact lists (host.walk_contact_lists): what a host controller hands to cmpc_solve_ticks_host / cmpc_populate
+        ts = tick_stride(N)
+        tk = np.zeros((B, ts))
+        tk[:, 0:3], tk[:, 3:6], tk[:, 6:9] = com0, dcom0, h0
+        if push is not None:
+            tk[:, 9:12] = np.asarray(push, dtype=np.float64).reshape(B, 3)
+        tk[:, 15] = 1.0 if step_adjust else 0.0
+        tk[:, 17:17 + 3 * (N + 1)] = comref.reshape(B, -1)
+        dTns = float(round(dT * 1e9))
+        sidx = np.arange(nsteps)
+        on = np.zeros((NC, nsteps))
+        off = np.zeros((NC, nsteps))
+        on[0], off[0] = sidx * P, sidx * P + P - ss
+        on[1], off[1] = (sidx - 1) * P + ds + ss, sidx * P + ds
+        on[:, 0] = -np.inf                                            # the first footstep was always there
+        for c in range(NC):
+            base = 17 + 6 * (N + 1) + 85 * c
+            s0 = (on[c][None, :] <= ph[:, None]).sum(axis=1) - 1     # the last footstep that started at or before knot 0
+            cnt = np.minimum(4, nsteps - s0)
+            tk[:, base] = cnt
+            for j in range(4):
+                sj = np.minimum(s0 + j, nsteps - 1)
+                ok = j < cnt
+                rec = np.zeros((B, 14))
+                rec[:, 0] = np.where(np.isinf(on[c][sj]), -1e18, (on[c][sj] - ph) * dTns)
+                rec[:, 1] = (off[c][sj] - ph) * dTns
+                rec[:, 2], rec[:, 3] = fx[c][sj], fy[c]
+                yj = yaw[c][bi, sj]
+                cy, sy = np.cos(yj), np.sin(yj)
+                rec[:, 5], rec[:, 6], rec[:, 8], rec[:, 9], rec[:, 13] = cy, sy, -sy, cy, 1.0
+                tk[:, base + 1 + 14 * j:base + 15 + 14 * j] = np.where(ok[:, None], rec, 0.0)
+        out["ticks"] = tk
+    return out
+
+
+def tick_stride(N: int) -> int:
+    """doubles per tick record (cmpc_tick_stride of include/cmpc_b200.h)"""
+    return 6 * N + 194
 
 
 def scenario_s0(dcom0=(0.0, 0.0, 0.0)):

@@ -120,3 +120,35 @@ def test_resample_linear_matches_numpy(H):
     assert np.allclose(H.resample_linear(t_in, p_in, [-1.0, 100.0]), [p_in[0], p_in[-1]])   # end points are held
     with pytest.raises(ValueError):
         H.resample_linear([0.0, 0.0], p_in[:2], t_out)                                       # times must increase
+
+
+@pytest.mark.parametrize("phase", [0, 3, 4, 7, 8, 11, 15, 21])
+def test_tick_record_matches_the_synthetic_workloads(H, workloads, phase):
+    """the compact tick record the C++ operator uploads (state, references, contact windows; expanded on the device by
+    cmpc_populate) against the record workloads.walk_batch(ticks=True) writes for the same instance"""
+    N = 12
+    w = workloads.walk_batch(N=N, B=1, seed=3, phase=phase, state_noise=1.0, ticks=True)
+    L = pkg("layout").Layout(N)
+    p, tk = w["p"][0], w["ticks"][0]
+    m = H.CentroidalMPCHost(os.path.join(DATA, "ergocub", "centroidal_mpc.ini"), "")
+    g0 = L.p_glob()
+    assert m.set_state(p[g0:g0 + 3], p[g0 + 3:g0 + 6], p[g0 + 6:g0 + 9], wrench=[0.5, -1.0, 0.25, 0.01, 0.02, 0.03])
+    assert m.set_reference_trajectory(p[L.p_comref(0):L.p_comref(0) + 3 * (N + 1)], p[L.p_href(0):L.p_href(0) + 3 * (N + 1)])
+    assert m.set_contact_phase_list(H.walk_contact_lists(phase))
+    t = m.tick_record()
+    assert t.shape == tk.shape == (workloads.tick_stride(N),)
+    assert np.array_equal(t[0:9], tk[0:9]) and np.allclose(t[9:15], [0.5, -1.0, 0.25, 0.01, 0.02, 0.03]) and t[15] == 1.0
+    assert np.array_equal(t[17:17 + 6 * (N + 1)], tk[17:17 + 6 * (N + 1)])
+    horizon_ns = N * 1e8
+    for c in range(2):
+        base = 17 + 6 * (N + 1) + 85 * c
+        n_cpp, n_np = int(t[base]), int(tk[base])
+        assert 1 <= n_cpp <= 6
+        rec = lambda a, j: a[base + 1 + 14 * j:base + 15 + 14 * j]  # noqa: E731
+        # same window start (the contact the foot stands / last stood on); the C++ window ends with the first contact that
+        # starts after the horizon, the numpy one always holds four
+        for j in range(min(n_cpp, n_np)):
+            a, b = rec(t, j), rec(tk, j)
+            assert a[0] == b[0] or (a[0] < -1e10 and b[0] < -1e10), (c, j, a[0], b[0])    # "always there": any time far in the past
+            assert a[1] == b[1] and np.allclose(a[2:], b[2:], atol=1e-15), (c, j)
+        assert rec(t, n_cpp - 1)[0] > horizon_ns or n_cpp >= n_np
