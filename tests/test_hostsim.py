@@ -23,7 +23,8 @@ class DevConfig(C.Structure):
                 ("w_sym", C.c_double), ("w_rate", C.c_double * 3), ("corner", C.c_double * 24), ("fricA", C.c_double * 12),
                 ("tol", C.c_double), ("max_iter", C.c_int), ("mu_init", C.c_double), ("bound_relax", C.c_double),
                 ("bound_push", C.c_double), ("inf_bound", C.c_double), ("pc", C.c_int), ("mu_warm", C.c_double),
-                ("scal_max_grad", C.c_double), ("acc_tol", C.c_double), ("acc_iter", C.c_int)]
+                ("scal_max_grad", C.c_double), ("acc_tol", C.c_double), ("acc_iter", C.c_int),
+                ("box_lo", C.c_double * 6), ("box_up", C.c_double * 6)]
 
 
 @pytest.fixture(scope="module")
