@@ -10,7 +10,10 @@ states, step adjustment off, ipopt tolerance 1e-8 -- per GPU (weak scaling over 
 ipopt_tolerance of the workload's robot ini (iCub3: 1e-8; ergoCubGazeboV1_1: 1e-4); --mu-strategy selects the barrier update
 (mehrotra = library default, monotone = IPOPT's default path).
   value    : solves/s with inputs resident in HBM, CUDA-event time of the K steps (max over ranks)
-  e2e      : solves/s through cmpc_solve_host with pinned HOST buffers (H2D + solve + D2H inside the timed region)
+  e2e      : solves/s through cmpc_solve_ticks_host, the per-tick call of the drop-in host class, with pinned HOST buffers: the
+             compact tick records (state, references, contact windows) go up, the formal input is expanded on the device, the
+             solution comes back (H2D + populate + solve + D2H inside the timed region); e2e.formal_input = the same through
+             cmpc_solve_host with the full (p, lbg, ubg, x0) arrays
   roofline : executed FP64 flop / kernel time against the measured FP64 FMA peak (the kernel is FP64 CUDA-core
              bound; HBM numbers are given beside it to show that HBM is not the bound)
   cpu_baseline : the CPU oracle (restatement of the IPOPT solve) on the host cores, bounded sample, rank 0, N = 1 only
@@ -53,12 +56,12 @@ FP64_PEAK_FALLBACK_TFLOPS = 37.0  # vendor figure (HGX B200 296 TF / 8); used on
 def workload(name: str, pkg, wl, seed: int, batch: int = 0):
     if name == "icub3_b1024":
         cfg = pkg.icub3_config()
-        w = wl.walk_batch(N=15, dT=0.1, B=batch or 1024, seed=seed, state_noise=1.0, step_adjust=False)
+        w = wl.walk_batch(N=15, dT=0.1, B=batch or 1024, seed=seed, state_noise=1.0, step_adjust=False, ticks=True)
         ocfg = dict(N=15, w_com=(1.0, 1.0, 200.0), w_pos=200.0, w_sym=0.0,
                     corners=[[(0.08, 0.03, 0), (0.08, -0.03, 0), (-0.08, -0.03, 0), (-0.08, 0.03, 0)]] * 2)
     elif name == "ergocub_b65536":
         cfg = pkg.ergocub_config()
-        w = wl.walk_batch(N=12, dT=0.1, B=batch or 65536, seed=seed, state_noise=2.0, yaw_range=0.3, step_adjust=True)
+        w = wl.walk_batch(N=12, dT=0.1, B=batch or 65536, seed=seed, state_noise=2.0, yaw_range=0.3, step_adjust=True, ticks=True)
         ocfg = dict(N=12, w_pos=2000.0)
     else:
         raise SystemExit(f"unknown workload {name}")
@@ -232,15 +235,14 @@ def run_config3(pkg, wl, dev, local, rank, world, flush, total=65536):
     import torch
     import torch.distributed as dist
     B = total // world
-    w = wl.walk_batch(N=12, dT=0.1, B=B, seed=1000 + rank, state_noise=2.0, yaw_range=0.3, step_adjust=True)
+    w = wl.walk_batch(N=12, dT=0.1, B=B, seed=1000 + rank, state_noise=2.0, yaw_range=0.3, step_adjust=True, ticks=True)
     tens = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
     d_p, d_lbg, d_ubg, d_x0 = tens(w["p"]), tens(w["lbg"]), tens(w["ubg"]), tens(w["x0"])
     d_x = d_x0.clone()
-    h_p, h_lbg, h_ubg, h_x0 = pin(w["p"]), pin(w["lbg"]), pin(w["ubg"]), pin(w["x0"])
+    h_tk = pin(w["ticks"])
     m = d_lbg.shape[1]
     d_lam = torch.zeros(B, m, dtype=torch.float64, device=dev)
-    h_lam = torch.zeros(B, m, dtype=torch.float64).pin_memory()
     h_obj = torch.zeros(B, dtype=torch.float64).pin_memory()
     h_st, h_it = torch.zeros(B, dtype=torch.int32).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory()
     vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
@@ -268,17 +270,18 @@ def run_config3(pkg, wl, dev, local, rank, world, flush, total=65536):
         t_own = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
         t_dev = max_over_ranks(t_own, dev, world)
         st_h, it_h = status.cpu().numpy(), iters.cpu().numpy()
-        # end to end: the C-ABI call with pinned host buffers (H2D + solve + D2H + synchronisation inside the timed region)
-        h_xs = [h_x0.clone().pin_memory() for _ in range(3)]
-        solver.lib.cmpc_solve_host(solver.handle, B, vp(h_p), vp(h_lbg), vp(h_ubg), vp(h_xs[0]), vp(h_lam), vp(h_obj), vp(h_st), vp(h_it), 0)
+        # end to end: cmpc_solve_ticks_host with pinned host buffers (tick records up, populate + solve, x / obj / status /
+        # iterations back, synchronisation: all inside the timed region)
+        h_xs = [torch.zeros(B, d_x0.shape[1], dtype=torch.float64).pin_memory() for _ in range(3)]
+        solver.lib.cmpc_solve_ticks_host(solver.handle, B, vp(h_tk), 0, vp(h_xs[0]), None, vp(h_obj), vp(h_st), vp(h_it))
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         for j in (1, 2):
-            rc = solver.lib.cmpc_solve_host(solver.handle, B, vp(h_p), vp(h_lbg), vp(h_ubg), vp(h_xs[j]), vp(h_lam), vp(h_obj), vp(h_st),
-                                            vp(h_it), 0)
+            rc = solver.lib.cmpc_solve_ticks_host(solver.handle, B, vp(h_tk), 0, vp(h_xs[j]), None, vp(h_obj), vp(h_st), vp(h_it))
             assert rc == 0, rc
+        assert int((h_st.numpy() == 0).sum()) == int((st_h == 0).sum())
         t_e2e = max_over_ranks(time.perf_counter() - t0, dev, world)
         conv, it_sum = sum_over_ranks([float((st_h == 0).sum()), float(it_h.sum())], dev, world)
         it_max = max_over_ranks(float(it_h.max()), dev, world)
@@ -532,40 +535,54 @@ def main():
     if world > 1:
         dist.barrier()
 
-    # ---- end to end through the host-pointer C-ABI call with pinned host buffers
+    # ---- end to end through the host-pointer C-ABI calls with pinned host buffers
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
-    hws = [tuple(pin(wj[k]) for k in ("p", "lbg", "ubg", "x0")) for _, wj, _ in ws[:5]]
-    h_p, h_lbg, h_ubg, h_x0 = hws[0]
-    h_x, h_lam = torch.empty_like(h_x0).pin_memory(), torch.zeros(B, m, dtype=torch.float64).pin_memory()
-    h_obj = torch.zeros(B, dtype=torch.float64).pin_memory()
-    h_st, h_it = torch.zeros(B, dtype=torch.int32).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory()
     import ctypes as C
     vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
-
-    def e2e_step(hx, hw):
-        # hx: pinned host buffer holding the step's initial guess on entry and the solution on return (the C ABI solves in
-        # place); every timed step gets its own pre-filled buffer, so that the timed region is the call itself: H2D copies,
-        # solve, D2H copies, synchronisation
-        rc = solver.lib.cmpc_solve_host(solver.handle, B, vp(hw[0]), vp(hw[1]), vp(hw[2]), vp(hx), vp(h_lam), vp(h_obj),
-                                        vp(h_st), vp(h_it), 0)
-        assert rc == 0, rc
-    h_x.copy_(h_x0)
-    e2e_step(h_x, hws[0])
-    torch.cuda.synchronize()
+    h_obj = torch.zeros(B, dtype=torch.float64).pin_memory()
+    h_st, h_it = torch.zeros(B, dtype=torch.int32).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory()
+    h_x = torch.zeros(B, n, dtype=torch.float64).pin_memory()
     k_e2e = max(2, min(args.steps, 5))
-    # timed step j solves batch (j + 1) % len(hws); the last one is batch 0 into h_x (the parity report reads it)
-    order = [(j + 1) % len(hws) for j in range(k_e2e - 1)] + [0]
-    h_xs = [hws[b][3].clone().pin_memory() for b in order[:-1]] + [h_x]
-    h_x.copy_(h_x0)
+    # (1) the per-tick call of the host class: tick records up, x / obj / status / iterations back (cold start: no multipliers)
+    h_tk = [pin(wj["ticks"]) for _, wj, _ in ws[:5]]
+    order = [(j + 1) % len(h_tk) for j in range(k_e2e - 1)] + [0]   # the last timed step solves batch 0 into h_x (parity report)
+    h_xs = [torch.zeros(B, n, dtype=torch.float64).pin_memory() for _ in order[:-1]] + [h_x]
+
+    def ticks_step(hx, htk):
+        rc = solver.lib.cmpc_solve_ticks_host(solver.handle, B, vp(htk), 0, vp(hx), None, vp(h_obj), vp(h_st), vp(h_it))
+        assert rc == 0, rc
+    ticks_step(h_x, h_tk[0])
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for j in range(k_e2e):
-        e2e_step(h_xs[j], hws[order[j]])
+        ticks_step(h_xs[j], h_tk[order[j]])
     torch.cuda.synchronize()
     e2e_value = world * B * k_e2e / max_over_ranks(time.perf_counter() - t0, dev, world)
-    h2d = 8 * B * (npar + 2 * m + n)
-    d2h = 8 * B * (n + m + 1) + 8 * B
+    ts_ = solver.lib.cmpc_tick_stride(N)
+    h2d = 8 * B * ts_
+    d2h = 8 * B * (n + 1) + 8 * B
+    # (2) the same through cmpc_solve_host: the full formal input (p, lbg, ubg, x0) up, x and lam_g back
+    h_p, h_lbg, h_ubg, h_x0 = (pin(w[k]) for k in ("p", "lbg", "ubg", "x0"))
+    h_lam = torch.zeros(B, m, dtype=torch.float64).pin_memory()
+    h_xf = [h_x0.clone().pin_memory() for _ in range(3)]
+
+    def formal_step(hx):
+        rc = solver.lib.cmpc_solve_host(solver.handle, B, vp(h_p), vp(h_lbg), vp(h_ubg), vp(hx), vp(h_lam), vp(h_obj), vp(h_st), vp(h_it), 0)
+        assert rc == 0, rc
+    formal_step(h_xf[0])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for j in (1, 2):
+        formal_step(h_xf[j])
+    torch.cuda.synchronize()
+    e2e_formal = world * B * 2 / max_over_ranks(time.perf_counter() - t0, dev, world)
+    # leave batch 0's results of the ticks path in the host buffers for the parity report
+    ticks_step(h_x, h_tk[0])
+    torch.cuda.synchronize()
     geometry = solver.geometry()
     peak_tf, peak_src = FP64_PEAK_FALLBACK_TFLOPS, "fallback: vendor 37 TFLOP/s FP64 (no measured FP64 peak in MEASURED_PEAKS.json)"
     if rank == 0:
@@ -612,7 +629,10 @@ def main():
                             "solver_grid": geometry, "result_gather": args.gather, "different_batches": NB,
                             "kernel_ms_of_every_step_rank0": [round(v, 3) for v in step_ms]},
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": k_e2e, "api": "cmpc_solve_host (pinned host buffers)"},
+                    "steps": k_e2e, "api": "cmpc_solve_ticks_host (pinned host buffers): tick records up, populate + solve on the device, x / obj / status / iterations back",
+                    "formal_input": {"value": e2e_formal, "h2d_bytes_per_step": 8 * B * (npar + 2 * m + n),
+                                     "d2h_bytes_per_step": 8 * B * (n + m + 1) + 8 * B, "steps": 2,
+                                     "api": "cmpc_solve_host: p, lbg, ubg, x0 up, x / lam_g / obj / status / iterations back"}},
             "gpu_launches": int(launches),
             "latency": {"p50_single_solve_ms": float(np.median(lat)) if lat else None,
                         "p95_single_solve_ms": float(np.percentile(lat, 95)) if lat else None, "samples": len(lat),
