@@ -742,6 +742,7 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
     T.on = true;
     CMPC_LANES
         if (lane == 0) {
+            sweep_barriers_init(sm);
             works_carve(scratch, N, w);
             io.sd = w.sd; io.small = w.small; io.ric = w.ric; io.ceq = w.ceq; io.dz = w.dz; io.res = w.res; io.cmap = cmap;
         }
