@@ -26,6 +26,11 @@ for rep in range(3):
 s.lib.cmpc_debug_profile(out)
 names = ["setup", "kkt_pass", "barrier_pass", "backward", "forward (x2 with corrector)", "recover (+ affine pass)", "step", "refine", "line search", "accept",
          "corrector backward sweep", "  bw: F1 load", "  bw: F2 form", "  bw: F3 form", "  bw: factor", "  bw: syrk+store"]
+mode = os.environ.get("CMPC_PROF_MODE", "1")   # 2: slots 10..14 = sub-phases of the forward sweeps, 3: of the corrector backward sweep
+if mode == "2":
+    names[11:] = ["  fw: wait for the block", "  fw: t = Y dxi", "  fw: substitution chain + barrier", "  fw: next dxi", "  fw: -"]
+elif mode == "3":
+    names[11:] = ["  cb: wait + stage tables", "  cb: h_u", "  cb: substitution chain + barrier", "  cb: Y'z", "  cb: copy"]
 v = np.array(list(out[:10]) + [out[15]], dtype=np.float64)
 vb = np.array(out[10:15], dtype=np.float64)
 iters = float(it.sum().item())
