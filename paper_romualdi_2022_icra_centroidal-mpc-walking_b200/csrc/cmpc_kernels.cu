@@ -391,7 +391,7 @@ using namespace cmpc;
 static_assert(sizeof(ISmem) % 16 == 0, "teams of a CTA are laid out back to back in shared memory");
 // (team size, teams per CTA) -> kernel
 #define CMPC_FOR_EACH_KERNEL(X) X(32, 1, CMPC_CTAS_PER_SM) X(64, 1, CMPC_CTAS_PER_SM) X(96, 1, CMPC_CTAS_PER_SM) \
-    X(128, 1, CMPC_CTAS_PER_SM) X(96, 7, 1) X(96, 3, 2) X(64, 7, 1) X(128, 7, 1)
+    X(128, 1, CMPC_CTAS_PER_SM) X(96, 7, 1) X(96, 3, 2) X(64, 7, 1) X(128, 7, 1) X(192, 1, 1) X(256, 1, 1)
 static const void* team_kernel(int nt, int g)
 {
 #define X(NT, G, C) if (nt == NT && g == G) return (const void*)cmpc_solve_team_kernel<NT, G, C>;
@@ -576,6 +576,8 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
         if (e == cudaSuccess && h->latency_path) {
             e = cudaFuncSetAttribute((const void*)cmpc_solve_team_kernel<128, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ISmem));
             if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)cmpc_solve_team_kernel<128, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ISmem));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)cmpc_solve_team_kernel<256, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ISmem));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)cmpc_solve_team_kernel<256, 1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct(1));
             if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)cmpc_solve_team_kernel<128, 1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct(2));
             if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)cmpc_solve_team_kernel<128, 1, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct(4));
         }
@@ -647,7 +649,12 @@ int cmpc_solve_batched(cmpc_handle h, int batch, const double* d_p, const double
     // without a register cap (254 registers, two CTAs run as fast as one), up to 4 per SM the one compiled for 4 CTAs (128)
     if (h->latency_path && batch <= 4 * h->sm_count) {
         const int per_sm = (batch + h->sm_count - 1) / h->sm_count;
-        if (per_sm <= 2)
+        if (per_sm <= 1)   // one instance per SM: a team of 256 threads (8 warps share the tensor-core tiles, the element-wise passes
+                           // and the split dot products of the sweeps: 5.5 -> 4.3 ms for a cold iCub3 solve)
+            cmpc_solve_team_kernel<256, 1, 1><<<batch, 256, (int)sizeof(ISmem), st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj,
+                                                                                     d_status, d_iters, warm_duals, h->d_work,
+                                                                                     h->work_stride, h->d_counter, h->d_cmap, 1);
+        else if (per_sm <= 2)
             cmpc_solve_team_kernel<128, 1, 1><<<batch, 128, (int)sizeof(ISmem), st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj,
                                                                                      d_status, d_iters, warm_duals, h->d_work,
                                                                                      h->work_stride, h->d_counter, h->d_cmap, 1);
