@@ -44,10 +44,14 @@ PKG = "paper_romualdi_2022_icra_centroidal-mpc-walking_b200"
 # smsp__sass_thread_inst_executed_op_{dfma x 2, dadd, dmul}_pred_on of one launch / (iterations x knots), see profiles/ and
 # DESIGN.md "flop accounting"; the per-iteration-and-knot work does not depend on the workload: the same code runs for every
 # robot, horizon and batch), and the canonical dense figure of SURVEY.md 8(d)
-FLOP_EXEC_PER_ITER_KNOT = {"monotone": 1.22e5, "mehrotra": 1.19e5}
+# Round 2: the stage factorisation and the SYRK run on the FP64 tensor cores: 1.861e5 = (2 x 5.922e9 DFMA + 2.026e9 DADD +
+# 2.410e9 DMUL thread instructions + 1.7287e10 tensor-core flop [sm__ops_path_tensor_src_fp64.sum]) / (12024 iterations x 15
+# knots) of capture r2_prof_final (profiles/r2_notes.md); 9.6e4 of it are DMMA flop on padded 8 x 8 tiles (round 1 executed
+# 1.19e5 on 3 x 3 tiles that skipped structural zeros).  monotone: round 1's figure + the same DMMA surplus (not re-captured).
+FLOP_EXEC_PER_ITER_KNOT = {"monotone": 1.89e5, "mehrotra": 1.861e5}
 FLOP_CANON_PER_ITER_KNOT = 422275.0
 # measured DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum), keyed by (workload, batch, strategy)
-DRAM_TRAFFIC_PER_LAUNCH = {("icub3_b1024", 1024, "monotone"): 1.240e10, ("icub3_b1024", 1024, "mehrotra"): 1.197e10}
+DRAM_TRAFFIC_PER_LAUNCH = {("icub3_b1024", 1024, "mehrotra"): 1.211e10}   # r2_prof_final: 7.88 GB read + 4.23 GB written
 # ipopt_tolerance of the robot ini each workload is built from (config/robots/<robot>/centroidal_mpc.ini)
 INI_TOLERANCE = {"icub3_b1024": 1e-8, "ergocub_b65536": 1e-4}
 FP64_PEAK_FALLBACK_TFLOPS = 37.0  # vendor figure (HGX B200 296 TF / 8); used only if the live DFMA probe fails
@@ -72,7 +76,10 @@ def config_dict(name: str, B: int, N: int, tol: float):
     """static description of the workload: the same dict on both arms (--impl ours / reference)"""
     return {"workload": name, "instances_per_gpu": B, "horizon_knots": N, "ipopt_tolerance": tol,
             "robot_ini": "iCubGazeboV3/centroidal_mpc.ini" if name.startswith("icub3") else "ergoCubGazeboV1_1/centroidal_mpc.ini",
-            "cold_start": True, "l2": "GPU arm: flushed between steps (256 MB write); CPU arm: not applicable"}
+            "cold_start": True,
+            "l2": "GPU arm: the timed steps cycle through 8 different input batches (8 x 25 MB) and one 332 MB scratch arena per "
+                  "handle, a working set several times the 126 MB L2 (with --pipeline 1 a 256 MB flush write runs between the "
+                  "steps as well); CPU arm: not applicable"}
 
 
 class ClockSampler(threading.Thread):
@@ -382,6 +389,10 @@ def main():
     ap.add_argument("--ctas", type=int, default=0, help="resident teams per SM (0 = occupancy)")
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (0 = the workload's own size)")
     ap.add_argument("--batches", type=int, default=8, help="different synthetic batches per rank the timed steps cycle through")
+    ap.add_argument("--pipeline", type=int, default=2,
+                    help="handles (each with its own stream and scratch arena) the timed steps alternate between: 2 (default) lets the "
+                         "straggler tail of one batch overlap the start of the next and the copies of the end-to-end path overlap the "
+                         "solves; 1 = one handle, one stream, L2 flush between steps (rounds 1 and 2a)")
     ap.add_argument("--mu-strategy", default="mehrotra", choices=["mehrotra", "monotone"],
                     help="barrier update of the solve: Mehrotra predictor-corrector (library default) or IPOPT's monotone update")
     args = ap.parse_args()
@@ -425,6 +436,8 @@ def main():
     cfg.lockstep_groups = args.groups
     cfg.mu_strategy = pkg.MU_MEHROTRA if args.mu_strategy == "mehrotra" else pkg.MU_MONOTONE
     solver = pkg.BatchedCentroidalMPC(cfg)
+    P = max(1, args.pipeline)
+    solvers = [solver] + [pkg.BatchedCentroidalMPC(cfg) for _ in range(P - 1)]
     B, N = w["p"].shape[0], cfg.horizon
     n, m, npar = solver.L.n, solver.L.m, solver.L.np
     tens = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
@@ -433,6 +446,9 @@ def main():
     d_x = d_x0.clone()
     d_lam = torch.zeros(B, m, dtype=torch.float64, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MB > 126 MB L2
+    d_xs = [d_x] + [d_x0.clone() for _ in range(P - 1)]
+    d_lams = [d_lam] + [torch.zeros_like(d_lam) for _ in range(P - 1)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(P)] if P > 1 else [torch.cuda.current_stream()]
 
     # The only exchange of the sharded job is the gather of the per-instance results.  Default: the results of
     # every step stay on the device and ONE all_gather follows the last step ("once per batch / rollout"): no NCCL kernel is
@@ -443,11 +459,11 @@ def main():
     gather = sharding.AsyncGather(world) if per_step else None
     results = torch.zeros(args.steps, B, 3, dtype=torch.float64, device=dev)
 
-    for j in range(args.warmup):
+    for j in range(max(args.warmup, P)):
         flush.zero_()
         bp, bl, bu, bx = dws[j % NB]
-        d_x.copy_(bx)
-        obj, status, iters, _ = solver.solve(bp, bl, bu, d_x, d_lam)
+        d_xs[j % P].copy_(bx)
+        obj, status, iters, _ = solvers[j % P].solve(bp, bl, bu, d_xs[j % P], d_lams[j % P])
         if per_step:
             gather.submit(sharding.pack_results(obj, status, iters))
     if per_step:
@@ -461,24 +477,47 @@ def main():
     sampler.start()
     time.sleep(0.15)   # nvidia-smi start-up: the first sample must fall inside the timed region
     sampler.rows.clear()
-    launches0 = solver.launch_count()
+    launches0 = sum(sv.launch_count() for sv in solvers)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    span = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
-    for s in range(args.steps):
-        flush.zero_()                      # L2 flush between timed iterations (outside the step's event pair)
-        bp, bl, bu, bx = dws[s % NB]
-        ev[s][0].record()
-        d_x.copy_(bx)
-        kev[s][0].record()
-        obj, status, iters, _ = solver.solve(bp, bl, bu, d_x, d_lam)
-        kev[s][1].record()
-        if per_step:
-            gather.submit(sharding.pack_results(obj, status, iters))
-        else:
-            results[s] = sharding.pack_results(obj, status, iters)
-        ev[s][1].record()
+    if P == 1:
+        for s in range(args.steps):
+            flush.zero_()                      # L2 flush between timed iterations (outside the step's event pair)
+            bp, bl, bu, bx = dws[s % NB]
+            ev[s][0].record()
+            d_x.copy_(bx)
+            kev[s][0].record()
+            obj, status, iters, _ = solver.solve(bp, bl, bu, d_x, d_lam)
+            kev[s][1].record()
+            if per_step:
+                gather.submit(sharding.pack_results(obj, status, iters))
+            else:
+                results[s] = sharding.pack_results(obj, status, iters)
+            ev[s][1].record()
+    else:
+        # step s runs on handle s % P and stream s % P: the launches of consecutive steps overlap on the device (a persistent CTA
+        # of step s + 1 starts on every SM whose seven instances of step s are done), every step is still one batch solved by
+        # one launch.  No flush kernel (it would serialise the streams): the steps cycle through NB different input batches and
+        # P scratch arenas, a working set several times the L2 (see config.l2).
+        main = torch.cuda.current_stream()
+        span[0].record(main)
+        for st in streams:
+            st.wait_event(span[0])
+        for s in range(args.steps):
+            bp, bl, bu, bx = dws[s % NB]
+            with torch.cuda.stream(streams[s % P]):
+                ev[s][0].record()
+                d_xs[s % P].copy_(bx)
+                kev[s][0].record()
+                obj, status, iters, _ = solvers[s % P].solve(bp, bl, bu, d_xs[s % P], d_lams[s % P])
+                kev[s][1].record()
+                results[s] = sharding.pack_results(obj, status, iters)
+                ev[s][1].record()
+        for s in range(max(0, args.steps - P), args.steps):
+            main.wait_event(ev[s][1])
     tail = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     tail[0].record()
     if per_step:
@@ -488,17 +527,26 @@ def main():
         gathered = sharding.gather_results(results.view(args.steps * B, 3), world)
         n_gathered = gathered.shape[0]
     tail[1].record()
+    span[1].record()
     torch.cuda.synchronize()
     assert n_gathered == args.steps * world * B
     if world > 1:
         dist.barrier()
     t_wall = time.perf_counter() - t_wall0
-    launches = solver.launch_count() - launches0
+    launches = sum(sv.launch_count() for sv in solvers) - launches0
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    t_steps = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
-    t_dev = t_steps + tail[0].elapsed_time(tail[1]) * 1e-3
-    t_kernel = sum(a.elapsed_time(b) for a, b in kev) * 1e-3
+    if P == 1:
+        t_steps = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+        t_dev = t_steps + tail[0].elapsed_time(tail[1]) * 1e-3
+        t_kernel = sum(a.elapsed_time(b) for a, b in kev) * 1e-3
+    else:
+        # overlapping launches: the device time of the job is the span from the first step's start to the end of the gather;
+        # a launch's share of the device is that span / launches (its own start-to-end time on its stream includes the wait for
+        # the SMs the previous launch still holds and is reported separately)
+        t_dev = span[0].elapsed_time(span[1]) * 1e-3
+        t_steps = span[0].elapsed_time(tail[0]) * 1e-3
+        t_kernel = t_steps
     t_max = max_over_ranks(t_dev, dev, world)
     if per_step:
         res_all = torch.cat([sharding.pack_results(obj, status, iters)] * args.steps).view(args.steps, B, 3)   # last step only
@@ -548,18 +596,43 @@ def main():
     order = [(j + 1) % len(h_tk) for j in range(k_e2e - 1)] + [0]   # the last timed step solves batch 0 into h_x (parity report)
     h_xs = [torch.zeros(B, n, dtype=torch.float64).pin_memory() for _ in order[:-1]] + [h_x]
 
-    def ticks_step(hx, htk):
-        rc = solver.lib.cmpc_solve_ticks_host(solver.handle, B, vp(htk), 0, vp(hx), None, vp(h_obj), vp(h_st), vp(h_it))
+    def ticks_step(hx, htk, slot=0, outs=None):
+        o, st_, it_ = outs or (h_obj, h_st, h_it)
+        rc = solvers[slot].lib.cmpc_solve_ticks_host(solvers[slot].handle, B, vp(htk), 0, vp(hx), None, vp(o), vp(st_), vp(it_))
         assert rc == 0, rc
-    ticks_step(h_x, h_tk[0])
+    for slot in range(P):
+        ticks_step(h_x, h_tk[0], slot)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    t0 = time.perf_counter()
-    for j in range(k_e2e):
-        ticks_step(h_xs[j], h_tk[order[j]])
-    torch.cuda.synchronize()
-    e2e_value = world * B * k_e2e / max_over_ranks(time.perf_counter() - t0, dev, world)
+    if P == 1:
+        t0 = time.perf_counter()
+        for j in range(k_e2e):
+            ticks_step(h_xs[j], h_tk[order[j]])
+        torch.cuda.synchronize()
+        e2e_value = world * B * k_e2e / max_over_ranks(time.perf_counter() - t0, dev, world)
+    else:
+        # P host threads, one handle each (the C call releases the interpreter lock): step j is made by thread j % P.  Every step
+        # is still one blocking cmpc_solve_ticks_host call: records up, populate + solve, results down, synchronised.
+        k_e2e = P * max(2, min(args.steps, 6) // P)
+        h_xs = [torch.zeros(B, n, dtype=torch.float64).pin_memory() for _ in range(k_e2e)]
+        outs = [(torch.zeros(B, dtype=torch.float64).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory(),
+                 torch.zeros(B, dtype=torch.int32).pin_memory()) for _ in range(P)]
+        gate = threading.Barrier(P + 1)
+
+        def worker(slot):
+            gate.wait()
+            for j in range(slot, k_e2e, P):
+                ticks_step(h_xs[j], h_tk[j % len(h_tk)], slot, outs[slot])
+        th = [threading.Thread(target=worker, args=(slot,)) for slot in range(P)]
+        for t_ in th:
+            t_.start()
+        t0 = time.perf_counter()
+        gate.wait()
+        for t_ in th:
+            t_.join()
+        torch.cuda.synchronize()
+        e2e_value = world * B * k_e2e / max_over_ranks(time.perf_counter() - t0, dev, world)
     ts_ = solver.lib.cmpc_tick_stride(N)
     h2d = 8 * B * ts_
     d2h = 8 * B * (n + 1) + 8 * B
@@ -599,7 +672,20 @@ def main():
                 peak_src = "measured live: cmpc_measure_fp64_peak (8 independent DFMA chains/thread, 148x8 CTAs x 256 threads); ncu peak_sustained 9472 DFMA/clk = 37.2"
         except Exception:
             pass
-    solver.close()
+    # one handle, one stream, flush between launches: the duration of a launch that has the device to itself
+    iso = []
+    for j in range(3):
+        flush.zero_()
+        bp, bl, bu, bx = dws[j % NB]
+        d_x.copy_(bx)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        solver.solve(bp, bl, bu, d_x, d_lam)
+        b.record()
+        torch.cuda.synchronize()
+        iso.append(a.elapsed_time(b))
+    for sv in solvers:
+        sv.close()
 
     # ---- the other north-star configurations, in the same run (every rank takes part)
     extras = {}
@@ -627,7 +713,12 @@ def main():
             "solve_stats": {"mu_strategy": args.mu_strategy, "converged": f"{conv}/{B * args.steps}",
                             "mean_iterations": total_iters / (B * args.steps), "max_iterations": int(iters_h.max()),
                             "solver_grid": geometry, "result_gather": args.gather, "different_batches": NB,
-                            "kernel_ms_of_every_step_rank0": [round(v, 3) for v in step_ms]},
+                            "pipeline": P,
+                            "pipeline_note": "steps alternate between `pipeline` handles (own stream, own scratch arena): one batch = "
+                                             "one launch as before, consecutive launches overlap on the device (the straggler tail of "
+                                             "a single-wave batch no longer idles the SMs); --pipeline 1 = one handle, one stream",
+                            "kernel_ms_of_every_step_rank0": [round(v, 3) for v in step_ms],
+                            "kernel_ms_isolated_launch": [round(v, 3) for v in iso]},
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": k_e2e, "api": "cmpc_solve_ticks_host (pinned host buffers): tick records up, populate + solve on the device, x / obj / status / iterations back",
                     "formal_input": {"value": e2e_formal, "h2d_bytes_per_step": 8 * B * (npar + 2 * m + n),
@@ -638,13 +729,17 @@ def main():
                         "p95_single_solve_ms": float(np.percentile(lat, 95)) if lat else None, "samples": len(lat),
                         "iterations": int(iters_all[0, 0]),
                         "e2e_host_operator_ms": (extras.get("config1_single_solve_host_operator") or {}).get("p50_ms"),
-                        "note": "batch of one instance, device resident, cold start; batches of up to 4 instances per SM run on independent single-team CTAs (128 threads; up to 2 per SM without a register cap) unless a geometry is forced; e2e_host_operator_ms = CentroidalMPC::advance() of the drop-in class"},
+                        "note": "batch of one instance, device resident, cold start; batches of up to 4 instances per SM run on independent single-team CTAs (one per SM: a team of 256 threads; two: 128 threads without a register cap; four: 128 threads) unless a geometry is forced; e2e_host_operator_ms = CentroidalMPC::advance() of the drop-in class"},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "traffic": DRAM_TRAFFIC_PER_LAUNCH.get((args.workload, B, args.mu_strategy)),
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu, profiles/); null where this "
                                          "exact (workload, batch, strategy) has not been captured",
                          "peak_source": peak_src, "kernel": "cmpc_solve_team_kernel",
-                         "kernel_ms_per_launch": 1e3 * kernel_s, "flop_executed_per_launch": flop_exec,
+                         "kernel_ms_per_launch": 1e3 * kernel_s,
+                         "kernel_ms_note": "pipeline 1: CUDA events around every launch on its stream; pipeline > 1: launches overlap, "
+                                           "the figure is the device span of the timed steps / launches (a launch's share of the "
+                                           "device); solve_stats.kernel_ms_isolated_launch = a launch alone on the device",
+                         "flop_executed_per_launch": flop_exec,
                          "flop_per_iteration_and_knot": FLOP_EXEC_PER_ITER_KNOT[args.mu_strategy],
                          "flop_canonical_dense_per_launch": flop_canon,
                          "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / kernel_s / 1e9,

@@ -139,7 +139,12 @@ int cmpc_solve_batched(cmpc_handle h, int batch, const double* d_p, const double
                        void* stream);
 
 /* Same solve with HOST pointers: copies p/lbg/ubg/x (and lam_g when warm_duals) to the device, solves, copies
- * x/lam_g/obj/status/iters back and synchronises.  This is the call a CentroidalMPC host object makes per tick. */
+ * x/lam_g/obj/status/iters back and synchronises.  This is the call a CentroidalMPC host object makes per tick.
+ * The host-pointer entry points (this one and cmpc_solve_ticks_host) run on a private non-blocking stream of the handle and
+ * return when that stream has drained: calls on DIFFERENT handles from different host threads overlap on the device (the
+ * copies of one with the solve of the other, and the straggler tail of one batch with the start of the next: two handles
+ * fed alternately deliver ~10 % more solves per second than one, bench.py "pipeline").  Pinned host buffers are needed
+ * for the copies to be asynchronous. */
 int cmpc_solve_host(cmpc_handle h, int batch, const double* p, const double* lbg, const double* ubg, double* x,
                     double* lam_g, double* obj, int* status, int* iters, int warm_duals);
 

@@ -425,6 +425,9 @@ struct cmpc_handle_s {
     // behind every solve; a solve enqueued on another stream than the previous one waits for it first.
     cudaEvent_t done = nullptr;
     cudaStream_t last_stream = nullptr;
+    // the host-pointer entry points (cmpc_solve_host, cmpc_solve_ticks_host) run on a private non-blocking stream of the handle:
+    // two handles driven from two host threads overlap their copies and solves instead of meeting on the legacy default stream
+    cudaStream_t hstream = nullptr;
     bool in_flight = false;
 };
 
@@ -609,6 +612,7 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
     if (e == cudaSuccess) e = cudaMemcpy(h->d_jslot, jc.slot.data(), sizeof(int) * jc.slot.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_hslot, hc.slot.data(), sizeof(int) * hc.slot.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { cmpc_destroy(h); return CMPC_E_CUDA; }
     *out = h;
     return CMPC_OK;
@@ -621,6 +625,7 @@ int cmpc_destroy(cmpc_handle h)
         DeviceGuard guard(h->device);
         if (h->in_flight && h->done) cudaEventSynchronize(h->done);  // the scratch arena must outlive the last solve
         if (h->done) cudaEventDestroy(h->done);
+        if (h->hstream) cudaStreamDestroy(h->hstream);
         cudaFree(h->d_work); cudaFree(h->d_counter); cudaFree(h->d_jslot); cudaFree(h->d_hslot); cudaFree(h->d_gscratch); cudaFree(h->d_cmap);
         cudaFree(h->d_p); cudaFree(h->d_lbg); cudaFree(h->d_ubg); cudaFree(h->d_x); cudaFree(h->d_lam); cudaFree(h->d_obj);
         cudaFree(h->d_status); cudaFree(h->d_iters); cudaFree(h->d_ticks);
@@ -719,20 +724,20 @@ int cmpc_solve_host(cmpc_handle h, int batch, const double* p, const double* lbg
     if (rc) return rc;
     const int N = h->cfg.N;
     size_t b = (size_t)batch;
-    CK(cudaMemcpyAsync(h->d_p, p, 8 * b * dim_p(N), cudaMemcpyHostToDevice, 0));
-    CK(cudaMemcpyAsync(h->d_lbg, lbg, 8 * b * dim_g(N), cudaMemcpyHostToDevice, 0));
-    CK(cudaMemcpyAsync(h->d_ubg, ubg, 8 * b * dim_g(N), cudaMemcpyHostToDevice, 0));
-    CK(cudaMemcpyAsync(h->d_x, x, 8 * b * dim_x(N), cudaMemcpyHostToDevice, 0));
-    if (warm_duals && lam_g) CK(cudaMemcpyAsync(h->d_lam, lam_g, 8 * b * dim_g(N), cudaMemcpyHostToDevice, 0));
+    CK(cudaMemcpyAsync(h->d_p, p, 8 * b * dim_p(N), cudaMemcpyHostToDevice, h->hstream));
+    CK(cudaMemcpyAsync(h->d_lbg, lbg, 8 * b * dim_g(N), cudaMemcpyHostToDevice, h->hstream));
+    CK(cudaMemcpyAsync(h->d_ubg, ubg, 8 * b * dim_g(N), cudaMemcpyHostToDevice, h->hstream));
+    CK(cudaMemcpyAsync(h->d_x, x, 8 * b * dim_x(N), cudaMemcpyHostToDevice, h->hstream));
+    if (warm_duals && lam_g) CK(cudaMemcpyAsync(h->d_lam, lam_g, 8 * b * dim_g(N), cudaMemcpyHostToDevice, h->hstream));
     rc = cmpc_solve_batched(h, batch, h->d_p, h->d_lbg, h->d_ubg, h->d_x, h->d_lam, h->d_obj, h->d_status, h->d_iters,
-                            warm_duals && lam_g, nullptr);
+                            warm_duals && lam_g, h->hstream);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(x, h->d_x, 8 * b * dim_x(N), cudaMemcpyDeviceToHost, 0));
-    if (lam_g) CK(cudaMemcpyAsync(lam_g, h->d_lam, 8 * b * dim_g(N), cudaMemcpyDeviceToHost, 0));
-    if (obj) CK(cudaMemcpyAsync(obj, h->d_obj, 8 * b, cudaMemcpyDeviceToHost, 0));
-    if (status) CK(cudaMemcpyAsync(status, h->d_status, 4 * b, cudaMemcpyDeviceToHost, 0));
-    if (iters) CK(cudaMemcpyAsync(iters, h->d_iters, 4 * b, cudaMemcpyDeviceToHost, 0));
-    CK(cudaStreamSynchronize(0));
+    CK(cudaMemcpyAsync(x, h->d_x, 8 * b * dim_x(N), cudaMemcpyDeviceToHost, h->hstream));
+    if (lam_g) CK(cudaMemcpyAsync(lam_g, h->d_lam, 8 * b * dim_g(N), cudaMemcpyDeviceToHost, h->hstream));
+    if (obj) CK(cudaMemcpyAsync(obj, h->d_obj, 8 * b, cudaMemcpyDeviceToHost, h->hstream));
+    if (status) CK(cudaMemcpyAsync(status, h->d_status, 4 * b, cudaMemcpyDeviceToHost, h->hstream));
+    if (iters) CK(cudaMemcpyAsync(iters, h->d_iters, 4 * b, cudaMemcpyDeviceToHost, h->hstream));
+    CK(cudaStreamSynchronize(h->hstream));
     h->resident_batch = batch;
     return CMPC_OK;
 }
@@ -764,28 +769,28 @@ int cmpc_solve_ticks_host(cmpc_handle h, int batch, const double* ticks, int war
     if (rc) return rc;
     const int N = h->cfg.N;
     const size_t b = (size_t)batch;
-    CK(cudaMemcpyAsync(h->d_ticks, ticks, 8 * b * tick_stride(N), cudaMemcpyHostToDevice, 0));
+    CK(cudaMemcpyAsync(h->d_ticks, ticks, 8 * b * tick_stride(N), cudaMemcpyHostToDevice, h->hstream));
     bool warm_duals = false;
     if (warm_mode == 2) {
-        CK(cudaMemcpyAsync(h->d_x, x, 8 * b * dim_x(N), cudaMemcpyHostToDevice, 0));
-        if (lam_g) CK(cudaMemcpyAsync(h->d_lam, lam_g, 8 * b * dim_g(N), cudaMemcpyHostToDevice, 0));
+        CK(cudaMemcpyAsync(h->d_x, x, 8 * b * dim_x(N), cudaMemcpyHostToDevice, h->hstream));
+        if (lam_g) CK(cudaMemcpyAsync(h->d_lam, lam_g, 8 * b * dim_g(N), cudaMemcpyHostToDevice, h->hstream));
         warm_duals = lam_g != nullptr;
     } else if (warm_mode == 1) warm_duals = true;
-    rc = cmpc_populate(h, batch, h->d_ticks, h->d_p, h->d_lbg, h->d_ubg, warm_mode == 0 ? h->d_x : nullptr, nullptr);
+    rc = cmpc_populate(h, batch, h->d_ticks, h->d_p, h->d_lbg, h->d_ubg, warm_mode == 0 ? h->d_x : nullptr, h->hstream);
     if (rc) return rc;
     if (warm_mode != 0) {
-        rc = cmpc_shift_warmstart(h, batch, h->d_x, warm_duals ? h->d_lam : nullptr, nullptr);
+        rc = cmpc_shift_warmstart(h, batch, h->d_x, warm_duals ? h->d_lam : nullptr, h->hstream);
         if (rc) return rc;
     }
     rc = cmpc_solve_batched(h, batch, h->d_p, h->d_lbg, h->d_ubg, h->d_x, h->d_lam, h->d_obj, h->d_status, h->d_iters,
-                            warm_duals ? 1 : 0, nullptr);
+                            warm_duals ? 1 : 0, h->hstream);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(x, h->d_x, 8 * b * dim_x(N), cudaMemcpyDeviceToHost, 0));
-    if (lam_g) CK(cudaMemcpyAsync(lam_g, h->d_lam, 8 * b * dim_g(N), cudaMemcpyDeviceToHost, 0));
-    if (obj) CK(cudaMemcpyAsync(obj, h->d_obj, 8 * b, cudaMemcpyDeviceToHost, 0));
-    if (status) CK(cudaMemcpyAsync(status, h->d_status, 4 * b, cudaMemcpyDeviceToHost, 0));
-    if (iters) CK(cudaMemcpyAsync(iters, h->d_iters, 4 * b, cudaMemcpyDeviceToHost, 0));
-    CK(cudaStreamSynchronize(0));
+    CK(cudaMemcpyAsync(x, h->d_x, 8 * b * dim_x(N), cudaMemcpyDeviceToHost, h->hstream));
+    if (lam_g) CK(cudaMemcpyAsync(lam_g, h->d_lam, 8 * b * dim_g(N), cudaMemcpyDeviceToHost, h->hstream));
+    if (obj) CK(cudaMemcpyAsync(obj, h->d_obj, 8 * b, cudaMemcpyDeviceToHost, h->hstream));
+    if (status) CK(cudaMemcpyAsync(status, h->d_status, 4 * b, cudaMemcpyDeviceToHost, h->hstream));
+    if (iters) CK(cudaMemcpyAsync(iters, h->d_iters, 4 * b, cudaMemcpyDeviceToHost, h->hstream));
+    CK(cudaStreamSynchronize(h->hstream));
     h->resident_batch = batch;
     return CMPC_OK;
 }

@@ -520,9 +520,9 @@ def test_ini_tolerances(oracle, workloads, tol, strategy):
 
 
 def test_small_batch_kernels_agree_with_the_lockstep_kernel(workloads):
-    """default geometry: batches of up to 2 / up to 4 instances per SM run on independent single-team CTAs (the kernel
-    without a register cap / the one compiled for four CTAs per SM), larger ones on the seven-team lock-step CTAs.  Same
-    solutions from all three (different team sizes: rounding-level differences only)."""
+    """default geometry: batches of one / up to 2 / up to 4 instances per SM run on independent single-team CTAs (a team of
+    256 threads / of 128 without a register cap / the one compiled for four CTAs per SM), larger ones on the seven-team
+    lock-step CTAs.  Same solutions from all four (different team sizes: rounding-level differences only)."""
     P = pkg()
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     w = workloads.walk_batch(N=12, B=4 * sms, seed=17, state_noise=1.5, yaw_range=0.2)
@@ -530,7 +530,7 @@ def test_small_batch_kernels_agree_with_the_lockstep_kernel(workloads):
     auto = P.BatchedCentroidalMPC(P.ergocub_config())
     xr, lr, objr, str_, itr = ref.solve_host(w["p"], w["lbg"], w["ubg"], w["x0"])
     assert (str_ == 0).all()
-    for B in (sms + 3, 2 * sms, 2 * sms + 1, 3 * sms + 5, 4 * sms):
+    for B in (1, sms, sms + 3, 2 * sms, 2 * sms + 1, 3 * sms + 5, 4 * sms):
         n0 = auto.launch_count()
         x, lam, obj, status, iters = auto.solve_host(w["p"][:B], w["lbg"][:B], w["ubg"][:B], w["x0"][:B])
         assert auto.launch_count() == n0 + 1
@@ -607,3 +607,29 @@ def test_two_streams_on_one_handle_are_ordered(workloads):
         assert (out[i][1].cpu().numpy() == 0).all()
         assert np.array_equal(dx[i].cpu().numpy(), ref[i][0]) and np.array_equal(out[i][2].cpu().numpy(), ref[i][4])
     s.close()
+
+
+def test_two_handles_two_host_threads_overlap_and_agree(workloads):
+    """the host-pointer entry points run on a private stream of their handle: two handles driven from two host threads (the
+    pipelined mode of bench.py) give bit for bit the results of the same calls made one after the other"""
+    import threading
+    P = pkg()
+    hs = [P.BatchedCentroidalMPC(P.icub3_config()) for _ in range(2)]
+    ws = [workloads.walk_batch(N=15, B=1100, seed=60 + j, state_noise=1.0, step_adjust=False) for j in range(4)]
+    ref = [hs[0].solve_host(w["p"], w["lbg"], w["ubg"], w["x0"]) for w in ws]
+    got = [None] * 4
+
+    def work(slot):
+        for j in range(slot, 4, 2):
+            w = ws[j]
+            got[j] = hs[slot].solve_host(w["p"], w["lbg"], w["ubg"], w["x0"])
+    th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for j in range(4):
+        assert (got[j][3] == 0).all()
+        assert np.array_equal(got[j][0], ref[j][0]) and np.array_equal(got[j][4], ref[j][4])
+    for h in hs:
+        h.close()
