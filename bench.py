@@ -389,8 +389,8 @@ def main():
     ap.add_argument("--ctas", type=int, default=0, help="resident teams per SM (0 = occupancy)")
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (0 = the workload's own size)")
     ap.add_argument("--batches", type=int, default=8, help="different synthetic batches per rank the timed steps cycle through")
-    ap.add_argument("--pipeline", type=int, default=2,
-                    help="handles (each with its own stream and scratch arena) the timed steps alternate between: 2 (default) lets the "
+    ap.add_argument("--pipeline", type=int, default=3,
+                    help="handles (each with its own stream and scratch arena) the timed steps alternate between: 3 (default; 2 and 4 measured too) lets the "
                          "straggler tail of one batch overlap the start of the next and the copies of the end-to-end path overlap the "
                          "solves; 1 = one handle, one stream, L2 flush between steps (rounds 1 and 2a)")
     ap.add_argument("--mu-strategy", default="mehrotra", choices=["mehrotra", "monotone"],
@@ -462,8 +462,12 @@ def main():
     for j in range(max(args.warmup, P)):
         flush.zero_()
         bp, bl, bu, bx = dws[j % NB]
-        d_xs[j % P].copy_(bx)
-        obj, status, iters, _ = solvers[j % P].solve(bp, bl, bu, d_xs[j % P], d_lams[j % P])
+        with torch.cuda.stream(streams[j % P]):    # the stream the handle is timed on (first use of a stream is not free)
+            d_xs[j % P].copy_(bx)
+            obj, status, iters, _ = solvers[j % P].solve(bp, bl, bu, d_xs[j % P], d_lams[j % P])
+            if not per_step:
+                results[0] = sharding.pack_results(obj, status, iters)
+        torch.cuda.synchronize()
         if per_step:
             gather.submit(sharding.pack_results(obj, status, iters))
     if per_step:
@@ -475,7 +479,20 @@ def main():
         dist.barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.15)   # nvidia-smi start-up: the first sample must fall inside the timed region
+    # nvidia-smi start-up (NVML initialisation perturbs the device for a few ms: kept out of the timed region) -- spent on more
+    # untimed warm-up launches, not asleep: after 0.2 s of idling the first timed launch ran at ramping clocks (41 ms against 15)
+    # (until the sampler has delivered its first rows, i.e. nvidia-smi is up and looping; 3 s at most)
+    t_ready = time.perf_counter() + 3.0
+    j = 0
+    while time.perf_counter() < t_ready and (len(sampler.rows) < 3 or j < P):
+        bp, bl, bu, bx = dws[j % NB]
+        with torch.cuda.stream(streams[j % P]):
+            d_xs[j % P].copy_(bx)
+            solvers[j % P].solve(bp, bl, bu, d_xs[j % P], d_lams[j % P])
+        torch.cuda.synchronize()
+        j += 1
+    if world > 1:
+        dist.barrier()
     sampler.rows.clear()
     launches0 = sum(sv.launch_count() for sv in solvers)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -621,7 +638,8 @@ def main():
         gate = threading.Barrier(P + 1)
 
         def worker(slot):
-            gate.wait()
+            torch.cuda.set_device(local)   # the current device is per host thread: without this the library's device guard would
+            gate.wait()                    # restore "device 0" after every call and create a context there on ranks > 0
             for j in range(slot, k_e2e, P):
                 ticks_step(h_xs[j], h_tk[j % len(h_tk)], slot, outs[slot])
         th = [threading.Thread(target=worker, args=(slot,)) for slot in range(P)]

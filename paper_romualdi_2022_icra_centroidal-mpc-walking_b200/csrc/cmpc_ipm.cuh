@@ -35,7 +35,15 @@ namespace cmpc {
 // invariant in the inner loop over the knots and hoisted out of it, the knot index is uniform over the warp, and the loads of
 // consecutive knots are independent of each other (the passes are bound by their instruction count: profiles/r1_notes.md)
 #define CMPC_ROLES(nroles) for (int r = lane & 31; r < (nroles); r += 32)
-#define CMPC_KNOTS(kfirst, klast) for (int k = (kfirst) + (lane >> 5); k <= (klast); k += (NT >= 32 ? NT / 32 : 1))
+#ifndef CMPC_KNOTS_UNROLL
+#define CMPC_KNOTS_UNROLL 1
+#endif
+#if defined(__CUDA_ARCH__) && CMPC_KNOTS_UNROLL > 1
+#define CMPC_KNOTS_PRAGMA _Pragma("unroll 2")
+#else
+#define CMPC_KNOTS_PRAGMA
+#endif
+#define CMPC_KNOTS(kfirst, klast) CMPC_KNOTS_PRAGMA for (int k = (kfirst) + (lane >> 5); k <= (klast); k += (NT >= 32 ? NT / 32 : 1))
 
 // the per-variable entry functions: inlined into the role-major loops (role decoding hoisted) or shared out-of-line copies
 #ifndef CMPC_INLINE_ENTRIES
