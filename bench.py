@@ -617,7 +617,12 @@ def main():
         o, st_, it_ = outs or (h_obj, h_st, h_it)
         rc = solvers[slot].lib.cmpc_solve_ticks_host(solvers[slot].handle, B, vp(htk), 0, vp(hx), None, vp(o), vp(st_), vp(it_))
         assert rc == 0, rc
-    for slot in range(P):
+    # the end-to-end path keeps more calls in flight than the device-resident loop (every call ends with a host synchronisation:
+    # a handle idles between the return of one call and the arrival of the next): 2 P handles / host threads
+    E = 1 if P == 1 else 2 * P
+    while len(solvers) < E:
+        solvers.append(pkg.BatchedCentroidalMPC(cfg))
+    for slot in range(E):
         ticks_step(h_x, h_tk[0], slot)
     torch.cuda.synchronize()
     if world > 1:
@@ -631,18 +636,18 @@ def main():
     else:
         # P host threads, one handle each (the C call releases the interpreter lock): step j is made by thread j % P.  Every step
         # is still one blocking cmpc_solve_ticks_host call: records up, populate + solve, results down, synchronised.
-        k_e2e = P * max(2, min(args.steps, 6) // P)
+        k_e2e = E * max(2, min(args.steps, 12) // E)
         h_xs = [torch.zeros(B, n, dtype=torch.float64).pin_memory() for _ in range(k_e2e)]
         outs = [(torch.zeros(B, dtype=torch.float64).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory(),
-                 torch.zeros(B, dtype=torch.int32).pin_memory()) for _ in range(P)]
-        gate = threading.Barrier(P + 1)
+                 torch.zeros(B, dtype=torch.int32).pin_memory()) for _ in range(E)]
+        gate = threading.Barrier(E + 1)
 
         def worker(slot):
             torch.cuda.set_device(local)   # the current device is per host thread: without this the library's device guard would
             gate.wait()                    # restore "device 0" after every call and create a context there on ranks > 0
-            for j in range(slot, k_e2e, P):
+            for j in range(slot, k_e2e, E):
                 ticks_step(h_xs[j], h_tk[j % len(h_tk)], slot, outs[slot])
-        th = [threading.Thread(target=worker, args=(slot,)) for slot in range(P)]
+        th = [threading.Thread(target=worker, args=(slot,)) for slot in range(E)]
         for t_ in th:
             t_.start()
         t0 = time.perf_counter()
@@ -738,7 +743,8 @@ def main():
                             "kernel_ms_of_every_step_rank0": [round(v, 3) for v in step_ms],
                             "kernel_ms_isolated_launch": [round(v, 3) for v in iso]},
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": k_e2e, "api": "cmpc_solve_ticks_host (pinned host buffers): tick records up, populate + solve on the device, x / obj / status / iterations back",
+                    "steps": k_e2e, "host_threads": E,
+                    "api": "cmpc_solve_ticks_host (pinned host buffers): tick records up, populate + solve on the device, x / obj / status / iterations back; one blocking call per step, `host_threads` threads with a handle each",
                     "formal_input": {"value": e2e_formal, "h2d_bytes_per_step": 8 * B * (npar + 2 * m + n),
                                      "d2h_bytes_per_step": 8 * B * (n + m + 1) + 8 * B, "steps": 2,
                                      "api": "cmpc_solve_host: p, lbg, ubg, x0 up, x / lam_g / obj / status / iterations back"}},
