@@ -72,11 +72,11 @@ struct WorkS {
     double *small;                                                                    // (N + 1) * SMALL_STRIDE
     double *ric;                                                                      // N * WRIC_STRIDE
 };
-CMPC_HD int works_doubles(int N)
+CMPC_HD int works_vector_doubles(int N)   // everything but the factor blocks
 {
-    return 5 * (N + 1) * ZS + 6 * (N + 1) * ES + 17 * N * PS + (N + 1) * TS + N * (SD_STRIDE + AWS + 8) + (N + 1) * SMALL_STRIDE
-           + N * WRIC_STRIDE;
+    return 5 * (N + 1) * ZS + 6 * (N + 1) * ES + 17 * N * PS + (N + 1) * TS + N * (SD_STRIDE + AWS + 8) + (N + 1) * SMALL_STRIDE;
 }
+CMPC_HD int works_doubles(int N) { return works_vector_doubles(N) + N * WRIC_STRIDE; }
 CMPC_HD void works_carve(double* base, int N, WorkS& w)
 {
     double* c = base;
@@ -741,7 +741,7 @@ template <int NT, int G, class Cta>
 CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem& ism, const unsigned short* cmap, int batch,
                      const double* p_all, const double* lbg_all, const double* ubg_all, double* x_all, double* lam_all,
                      double* obj_all, int* status_all, int* iters_all, int warm_duals, unsigned int* counter,
-                     int first_inst = 0, int queue_base = 1)
+                     int first_inst = 0, int queue_base = 1, double* ric_region = nullptr)
 {
     const int N = cfg.N, n = dim_x(N), np = dim_p(N), m = dim_g(N);
     WSmem& sm = ism.sw;
@@ -752,6 +752,7 @@ CMPC_HD void ipm_run(Team T, Cta& cta, const Config& cfg, double* scratch, ISmem
         if (lane == 0) {
             sweep_barriers_init(sm);
             works_carve(scratch, N, w);
+            if (ric_region) w.ric = ric_region;   // the factor blocks of all teams live apart from the iterate vectors (L2 window)
             io.sd = w.sd; io.small = w.small; io.ric = w.ric; io.ceq = w.ceq; io.dz = w.dz; io.res = w.res; io.cmap = cmap;
         }
     CMPC_LANES_END

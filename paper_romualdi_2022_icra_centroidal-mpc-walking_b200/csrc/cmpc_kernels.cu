@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(NT * G, CTAS)
 cmpc_solve_team_kernel(const __grid_constant__ Config cfg, int batch, const double* __restrict__ p,
                        const double* __restrict__ lbg, const double* __restrict__ ubg, double* x, double* lam, double* obj,
                        int* status, int* iters, int warm_duals, double* work, size_t work_stride, unsigned int* counter,
-                       const unsigned short* __restrict__ cmap, int ngroups)
+                       const unsigned short* __restrict__ cmap, int ngroups, double* ric, size_t ric_stride)
 {
     extern __shared__ __align__(16) double smem_raw[];
     const int team = threadIdx.x / NT;
@@ -175,9 +175,10 @@ cmpc_solve_team_kernel(const __grid_constant__ Config cfg, int batch, const doub
     typename TeamCta<NT, G>::type cta;
     cta.tid = T.lane; cta.nt = NT; cta.warp = T.lane >> 5; cta.lane = T.lane & 31; cta.wsize = 32;
     if constexpr (!(NT == 32 && G == 1)) { cta.red = sm.sw.red; cta.bar = G > 1 ? team + 1 : 0; }
-    double* base = work + ((size_t)blockIdx.x * G + team) * work_stride;
+    const size_t slot = (size_t)blockIdx.x * G + team;
+    double* base = work + slot * work_stride;
     ipm_run<NT, G>(T, cta, cfg, base, sm, cmap, batch, p, lbg, ubg, x, lam, obj, status, iters, warm_duals, counter,
-                   team * (int)gridDim.x + (int)blockIdx.x, G * (int)gridDim.x);
+                   team * (int)gridDim.x + (int)blockIdx.x, G * (int)gridDim.x, ric + slot * ric_stride);
 }
 
 // warm-start shift: one CTA per instance, the vector is staged in shared memory so that loads and stores are coalesced
@@ -382,6 +383,17 @@ using namespace cmpc;
 #ifndef CMPC_CTAS_PER_SM
 #define CMPC_CTAS_PER_SM 7
 #endif
+#ifndef CMPC_L2_WINDOW
+#define CMPC_L2_WINDOW 0   // 1: persisting-L2 access window over the iterate vectors of the resident teams.  Measured (B200: 79 MB of
+                           // set-aside, 128 MB window): 74.0 k -> 71.8 k solves/s with the full set-aside, unchanged with half of it or
+                           // with 40 % (profiles/r2_notes.md): off
+#endif
+#ifndef CMPC_L2_MISS_NORMAL
+#define CMPC_L2_MISS_NORMAL 0
+#endif
+#ifndef CMPC_L2_FRACTION
+#define CMPC_L2_FRACTION 1.0
+#endif
 #ifndef CMPC_DEFAULT_GROUPS
 #define CMPC_DEFAULT_GROUPS 3     // independent lock-step groups per CTA (3 + 2 + 2 teams)
 #endif
@@ -407,8 +419,11 @@ struct cmpc_handle_s {
     bool latency_path = false;  // default geometry: batches of at most one instance per SM go to the single-team kernel
     int device = 0, sm_count = 0, lockstep = 1, threads = CMPC_DEFAULT_TEAM, ctas_per_sm = 0, grid = 0, smem = 0;
     int shift_smem = 0, eval_smem = 0;  // dynamic shared memory of the auxiliary kernels
-    size_t work_stride = 0, work_slots = 0;
-    double* d_work = nullptr;
+    size_t work_stride = 0, work_slots = 0, ric_stride = 0;
+    double* d_work = nullptr;   // [slots x work_stride] iterate vectors of every team, then [slots x ric_stride] factor blocks (d_ric)
+    double* d_ric = nullptr;
+    size_t l2_window_bytes = 0; // bytes of the vector region covered by the persisting-L2 access window (0: none)
+    float l2_hit_ratio = 0.f;
     unsigned int* d_counter = nullptr;
     int *d_jslot = nullptr, *d_hslot = nullptr;
     unsigned short* d_cmap = nullptr;
@@ -591,12 +606,13 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
         if (e != cudaSuccess) { h->last_cuda = (int)e; delete h; return CMPC_E_CUDA; }
     }
     h->grid = h->sm_count * h->ctas_per_sm;  // persistent grid: a multiple of the SM count
-    h->work_stride = ((size_t)works_doubles(c.N) + 15) & ~(size_t)15;
+    h->work_stride = ((size_t)works_vector_doubles(c.N) + 15) & ~(size_t)15;
+    h->ric_stride = ((size_t)c.N * WRIC_STRIDE + 15) & ~(size_t)15;
     h->work_slots = std::max((size_t)h->grid * h->lockstep, h->latency_path ? (size_t)4 * h->sm_count : (size_t)0);
     Csc jc, hc;
     build_csc(c.N, false, jc);
     build_csc(c.N, true, hc);
-    if (cudaMalloc(&h->d_work, sizeof(double) * h->work_stride * h->work_slots) != cudaSuccess ||
+    if (cudaMalloc(&h->d_work, sizeof(double) * (h->work_stride + h->ric_stride) * h->work_slots) != cudaSuccess ||
         cudaMalloc(&h->d_counter, sizeof(unsigned int)) != cudaSuccess ||
         cudaMalloc(&h->d_jslot, sizeof(int) * jc.slot.size()) != cudaSuccess ||
         cudaMalloc(&h->d_hslot, sizeof(int) * hc.slot.size()) != cudaSuccess ||
@@ -607,7 +623,22 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
     }
     std::vector<unsigned short> cm(CF_DINV);
     build_cmap(cm.data());
-    e = cudaMemset(h->d_work, 0, sizeof(double) * h->work_stride * h->work_slots);
+    h->d_ric = h->d_work + h->work_stride * h->work_slots;
+    e = cudaMemset(h->d_work, 0, sizeof(double) * (h->work_stride + h->ric_stride) * h->work_slots);
+#if CMPC_L2_WINDOW
+    // The iterate vectors of all resident teams (163 KB each at N = 15: more than the L2 for 1036 teams) are read and written by
+    // every element-wise pass of every iteration; the factor blocks stream through once per sweep.  A persisting-L2 access window
+    // over the vector region (hit ratio = what the set-aside can hold) keeps that fraction of the vectors resident instead of
+    // letting the whole set thrash.  Device-wide limit, set once; the window is a launch attribute of the solver kernel only.
+    if (e == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+        const size_t vec_bytes = sizeof(double) * h->work_stride * h->work_slots;
+        const size_t persist = std::min((size_t)(CMPC_L2_FRACTION * prop.persistingL2CacheMaxSize), vec_bytes);
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) == cudaSuccess) {
+            h->l2_window_bytes = std::min(vec_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+            h->l2_hit_ratio = (float)std::min(1.0, (double)persist / (double)h->l2_window_bytes);
+        } else cudaGetLastError();
+    }
+#endif
     if (e == cudaSuccess) e = cudaMemcpy(h->d_cmap, cm.data(), sizeof(unsigned short) * CF_DINV, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_jslot, jc.slot.data(), sizeof(int) * jc.slot.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_hslot, hc.slot.data(), sizeof(int) * hc.slot.size(), cudaMemcpyHostToDevice);
@@ -649,6 +680,19 @@ int cmpc_solve_batched(cmpc_handle h, int batch, const double* d_p, const double
     const bool capturing = cap != cudaStreamCaptureStatusNone;
     if (!capturing && h->in_flight && st != h->last_stream) CK(cudaStreamWaitEvent(st, h->done, 0));
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
+#if CMPC_L2_WINDOW
+    const bool window = h->l2_window_bytes > 0 && !capturing;
+    if (window) {
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof av);
+        av.accessPolicyWindow.base_ptr = h->d_work;
+        av.accessPolicyWindow.num_bytes = h->l2_window_bytes;
+        av.accessPolicyWindow.hitRatio = h->l2_hit_ratio;
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = CMPC_L2_MISS_NORMAL ? cudaAccessPropertyNormal : cudaAccessPropertyStreaming;
+        if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+    }
+#endif
     // small batches are latency bound: independent single-team CTAs of 128 threads (no lock-step, no 80-register cap) beat the
     // seven-team CTAs while at most four of them share an SM (profiles/r1_notes.md): up to 2 per SM the kernel compiled
     // without a register cap (254 registers, two CTAs run as fast as one), up to 4 per SM the one compiled for 4 CTAs (128)
@@ -658,27 +702,35 @@ int cmpc_solve_batched(cmpc_handle h, int batch, const double* d_p, const double
                            // and the split dot products of the sweeps: 5.5 -> 4.3 ms for a cold iCub3 solve)
             cmpc_solve_team_kernel<256, 1, 1><<<batch, 256, (int)sizeof(ISmem), st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj,
                                                                                      d_status, d_iters, warm_duals, h->d_work,
-                                                                                     h->work_stride, h->d_counter, h->d_cmap, 1);
+                                                                                     h->work_stride, h->d_counter, h->d_cmap, 1, h->d_ric, h->ric_stride);
         else if (per_sm <= 2)
             cmpc_solve_team_kernel<128, 1, 1><<<batch, 128, (int)sizeof(ISmem), st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj,
                                                                                      d_status, d_iters, warm_duals, h->d_work,
-                                                                                     h->work_stride, h->d_counter, h->d_cmap, 1);
+                                                                                     h->work_stride, h->d_counter, h->d_cmap, 1, h->d_ric, h->ric_stride);
         else
             cmpc_solve_team_kernel<128, 1, 4><<<batch, 128, (int)sizeof(ISmem), st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj,
                                                                                      d_status, d_iters, warm_duals, h->d_work,
-                                                                                     h->work_stride, h->d_counter, h->d_cmap, 1);
+                                                                                     h->work_stride, h->d_counter, h->d_cmap, 1, h->d_ric, h->ric_stride);
     } else {
         int grid = std::min(batch, h->grid);  // a small batch is spread over the SMs (static first instance: team * grid + CTA)
 #define X(NT, G, C)                                                                                                      \
     if (h->threads == NT && h->lockstep == G)                                                                            \
         cmpc_solve_team_kernel<NT, G, C><<<grid, NT * G, h->smem, st>>>(h->cfg, batch, d_p, d_lbg, d_ubg, d_x, d_lam_g, d_obj, \
                                                                         d_status, d_iters, warm_duals, h->d_work,         \
-                                                                        h->work_stride, h->d_counter, h->d_cmap, h->groups);
+                                                                        h->work_stride, h->d_counter, h->d_cmap, h->groups, h->d_ric, h->ric_stride);
         CMPC_FOR_EACH_KERNEL(X)
 #undef X
     }
     h->launches++;
     CK(cudaGetLastError());
+#if CMPC_L2_WINDOW
+    if (window) {   // the window belongs to this launch, not to whatever the caller enqueues on the stream next
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof av);
+        av.accessPolicyWindow.num_bytes = 0;
+        if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+    }
+#endif
     if (!capturing) {
         CK(cudaEventRecord(h->done, st));
         h->last_stream = st;

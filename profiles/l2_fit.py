@@ -1,6 +1,6 @@
 """Does the L2 residency of the per-team scratch bound the loaded SM?  Horizon sweep at one instance per resident team (batch
 1036) down to horizons whose whole scratch (iterate vectors + factors) fits the 126 MB L2: cost per knot and iteration.
-usage: python profiles/l2_fit.py [library.so]"""
+usage: python profiles/l2_fit.py [library.so] [N1,N2,...]"""
 import importlib
 import os
 import sys
@@ -23,7 +23,8 @@ def footprint(N):   # works_doubles of csrc/cmpc_ipm.cuh, bytes: (vectors, facto
 
 
 print(f"{'N':>3} {'ms':>8} {'iters':>6} {'us / (knot iteration)':>22} {'vectors MB':>11} {'factors MB':>11}   (1036 resident teams, L2 = 126 MB)")
-for N in (3, 4, 5, 6, 8, 10, 12, 15, 20):
+HORIZONS = tuple(int(a) for a in sys.argv[2].split(",")) if len(sys.argv) > 2 else (3, 4, 5, 6, 8, 10, 12, 15, 20)
+for N in HORIZONS:
     cfg = pkg.ergocub_config(horizon=N)
     s = pkg.BatchedCentroidalMPC(cfg)
     w = wl.walk_batch(N=N, dT=0.1, B=1036, seed=0, state_noise=1.0, yaw_range=0.2)
