@@ -178,7 +178,7 @@ cmpc_solve_team_kernel(const __grid_constant__ Config cfg, int batch, const doub
     const size_t slot = (size_t)blockIdx.x * G + team;
     double* base = work + slot * work_stride;
     ipm_run<NT, G>(T, cta, cfg, base, sm, cmap, batch, p, lbg, ubg, x, lam, obj, status, iters, warm_duals, counter,
-                   team * (int)gridDim.x + (int)blockIdx.x, G * (int)gridDim.x, ric + slot * ric_stride);
+                   team * (int)gridDim.x + (int)blockIdx.x, G * (int)gridDim.x, ric_stride ? ric + slot * ric_stride : nullptr);
 }
 
 // warm-start shift: one CTA per instance, the vector is staged in shared memory so that loads and stores are coalesced
@@ -387,6 +387,10 @@ using namespace cmpc;
 #define CMPC_L2_WINDOW 0   // 1: persisting-L2 access window over the iterate vectors of the resident teams.  Measured (B200: 79 MB of
                            // set-aside, 128 MB window): 74.0 k -> 71.8 k solves/s with the full set-aside, unchanged with half of it or
                            // with 40 % (profiles/r2_notes.md): off
+#endif
+#ifndef CMPC_SPLIT_RIC
+#define CMPC_SPLIT_RIC 1   // factor blocks of all teams in their own region of the arena (needed by the window; a hair faster: 90.0 k
+                           // against 89.9 k solves/s over three alternating runs each)
 #endif
 #ifndef CMPC_L2_MISS_NORMAL
 #define CMPC_L2_MISS_NORMAL 0
@@ -606,8 +610,13 @@ int cmpc_create(const cmpc_config* u, cmpc_handle* out)
         if (e != cudaSuccess) { h->last_cuda = (int)e; delete h; return CMPC_E_CUDA; }
     }
     h->grid = h->sm_count * h->ctas_per_sm;  // persistent grid: a multiple of the SM count
+#if CMPC_SPLIT_RIC
     h->work_stride = ((size_t)works_vector_doubles(c.N) + 15) & ~(size_t)15;
     h->ric_stride = ((size_t)c.N * WRIC_STRIDE + 15) & ~(size_t)15;
+#else
+    h->work_stride = ((size_t)works_doubles(c.N) + 15) & ~(size_t)15;   // factor blocks behind the vectors of their team
+    h->ric_stride = 0;
+#endif
     h->work_slots = std::max((size_t)h->grid * h->lockstep, h->latency_path ? (size_t)4 * h->sm_count : (size_t)0);
     Csc jc, hc;
     build_csc(c.N, false, jc);
