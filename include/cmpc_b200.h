@@ -74,7 +74,7 @@ typedef struct cmpc_config {
     double bound_push;                      /* IPOPT bound_push = bound_frac, default 0.01                          */
     double infinity;                        /* |bound| >= infinity means no bound, default 1e19                     */
     int device;                             /* CUDA device ordinal                                                  */
-    int threads_per_instance;               /* team size: 32, 64, 96 or 128 threads per instance, 0 = default (96)  */
+    int threads_per_instance;               /* team size: 32, 64, 96, 128 (192, 256: one team per CTA), 0 = default */
     int ctas_per_sm;                        /* resident CTAs per SM used to size the persistent grid, 0 = occupancy */
     int teams_per_cta;                      /* teams walking in lock-step through one CTA: 1, 3 or 7; 0 = default    */
     int lockstep_groups;                    /* independent lock-step groups the teams of a CTA form: 1 .. teams_per_cta, */
@@ -132,8 +132,10 @@ int cmpc_destroy(cmpc_handle h);
  * d_obj[batch], d_status[batch], d_iters[batch] may be null.  d_iters counts every interior-point iteration spent on
  * the instance (an instance handed from the predictor-corrector to the monotone path reports the sum).  `stream` is a
  * cudaStream_t (null = default stream); the call is asynchronous with respect to the host.  One kernel launch per call:
- * batches of up to 4 instances per SM run on independent single-team CTAs, larger ones on persistent CTAs of seven
- * teams walking in lock-step. */
+ * batches of up to 4 instances per SM run on independent single-team CTAs (one instance per SM: a team of 256 threads),
+ * larger ones on persistent CTAs of seven teams of 96 threads walking in lock-step.  A handle
+ * serialises its solves (one work queue, one scratch arena); launches of DIFFERENT handles on different streams overlap
+ * on the device: the straggler tail of a single-wave batch then no longer idles the SMs (bench.py --pipeline). */
 int cmpc_solve_batched(cmpc_handle h, int batch, const double* d_p, const double* d_lbg, const double* d_ubg,
                        double* d_x, double* d_lam_g, double* d_obj, int* d_status, int* d_iters, int warm_duals,
                        void* stream);
