@@ -664,18 +664,50 @@ def main():
     h_lam = torch.zeros(B, m, dtype=torch.float64).pin_memory()
     h_xf = [h_x0.clone().pin_memory() for _ in range(3)]
 
-    def formal_step(hx):
-        rc = solver.lib.cmpc_solve_host(solver.handle, B, vp(h_p), vp(h_lbg), vp(h_ubg), vp(hx), vp(h_lam), vp(h_obj), vp(h_st), vp(h_it), 0)
+    def formal_step(hx, slot=0, outs=None, hl=None):
+        o, st_, it_ = outs or (h_obj, h_st, h_it)
+        sv = solvers[slot]
+        rc = sv.lib.cmpc_solve_host(sv.handle, B, vp(h_p), vp(h_lbg), vp(h_ubg), vp(hx), vp(hl if hl is not None else h_lam), vp(o),
+                                    vp(st_), vp(it_), 0)
         assert rc == 0, rc
-    formal_step(h_xf[0])
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for j in (1, 2):
-        formal_step(h_xf[j])
-    torch.cuda.synchronize()
-    e2e_formal = world * B * 2 / max_over_ranks(time.perf_counter() - t0, dev, world)
+    k_formal = 2
+    if P == 1:
+        formal_step(h_xf[0])
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for j in (1, 2):
+            formal_step(h_xf[j])
+        torch.cuda.synchronize()
+        e2e_formal = world * B * 2 / max_over_ranks(time.perf_counter() - t0, dev, world)
+    else:
+        # same threads-and-handles arrangement as the tick-record path: E blocking calls in flight
+        k_formal = 2 * E
+        h_xf = [h_x0.clone().pin_memory() for _ in range(k_formal)]
+        h_lams = [torch.zeros(B, m, dtype=torch.float64).pin_memory() for _ in range(E)]
+        for slot in range(E):
+            formal_step(h_xf[slot], slot, outs[slot], h_lams[slot])
+            h_xf[slot].copy_(h_x0)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        gate2 = threading.Barrier(E + 1)
+
+        def fworker(slot):
+            torch.cuda.set_device(local)
+            gate2.wait()
+            for j in range(slot, k_formal, E):
+                formal_step(h_xf[j], slot, outs[slot], h_lams[slot])
+        th = [threading.Thread(target=fworker, args=(slot,)) for slot in range(E)]
+        for t_ in th:
+            t_.start()
+        t0 = time.perf_counter()
+        gate2.wait()
+        for t_ in th:
+            t_.join()
+        torch.cuda.synchronize()
+        e2e_formal = world * B * k_formal / max_over_ranks(time.perf_counter() - t0, dev, world)
     # leave batch 0's results of the ticks path in the host buffers for the parity report
     ticks_step(h_x, h_tk[0])
     torch.cuda.synchronize()
@@ -746,7 +778,7 @@ def main():
                     "steps": k_e2e, "host_threads": E,
                     "api": "cmpc_solve_ticks_host (pinned host buffers): tick records up, populate + solve on the device, x / obj / status / iterations back; one blocking call per step, `host_threads` threads with a handle each",
                     "formal_input": {"value": e2e_formal, "h2d_bytes_per_step": 8 * B * (npar + 2 * m + n),
-                                     "d2h_bytes_per_step": 8 * B * (n + m + 1) + 8 * B, "steps": 2,
+                                     "d2h_bytes_per_step": 8 * B * (n + m + 1) + 8 * B, "steps": k_formal,
                                      "api": "cmpc_solve_host: p, lbg, ubg, x0 up, x / lam_g / obj / status / iterations back"}},
             "gpu_launches": int(launches),
             "latency": {"p50_single_solve_ms": float(np.median(lat)) if lat else None,
