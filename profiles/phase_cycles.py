@@ -29,6 +29,8 @@ names = ["setup", "kkt_pass", "barrier_pass", "backward", "forward (x2 with corr
 mode = os.environ.get("CMPC_PROF_MODE", "1")   # 2: slots 10..14 = sub-phases of the forward sweeps, 3: of the corrector backward sweep
 if mode == "2":
     names[11:] = ["  fw: wait for the block", "  fw: t = Y dxi", "  fw: substitution chain + barrier", "  fw: next dxi", "  fw: -"]
+elif mode == "5":
+    names[11:] = ["  bw: F3a", "  bw: F3b + first diagonal block", "  bw: SYRK tiles (warp 0)", "  bw: factor stores + barrier", "  bw: copy + barrier"]
 elif mode == "4":
     names[11:] = ["  fa: first diagonal block", "  fa: 4 panels", "  fa: 3 trailing updates + look-ahead", "  fa: -", "  fa: -"]
 elif mode == "3":

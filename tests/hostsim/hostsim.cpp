@@ -60,6 +60,9 @@ static int solve_team(const cmpc::Config* cfg, const double* p, const double* lb
 extern "C" int hostsim_solve_team32(const cmpc::Config* cfg, const double* p, const double* lbg, const double* ubg, double* x,
                                     double* lam, int warm_duals, int* iters, double* obj, double* kkt)
 { return solve_team<32>(cfg, p, lbg, ubg, x, lam, warm_duals, iters, obj, kkt); }
+extern "C" int hostsim_solve_team96(const cmpc::Config* cfg, const double* p, const double* lbg, const double* ubg, double* x,
+                                    double* lam, int warm_duals, int* iters, double* obj, double* kkt)
+{ return solve_team<96>(cfg, p, lbg, ubg, x, lam, warm_duals, iters, obj, kkt); }
 extern "C" int hostsim_solve_team128(const cmpc::Config* cfg, const double* p, const double* lbg, const double* ubg, double* x,
                                      double* lam, int warm_duals, int* iters, double* obj, double* kkt)
 { return solve_team<128>(cfg, p, lbg, ubg, x, lam, warm_duals, iters, obj, kkt); }

@@ -66,7 +66,7 @@ def run(L, fn, c, w, b):
     return st, it.value, obj.value, x, lam
 
 
-@pytest.mark.parametrize("fn", ["hostsim_solve", "hostsim_solve_team32", "hostsim_solve_team128"])
+@pytest.mark.parametrize("fn", ["hostsim_solve", "hostsim_solve_team32", "hostsim_solve_team96", "hostsim_solve_team128"])
 @pytest.mark.parametrize("N,kw,wkw", [
     (12, dict(), dict(state_noise=1.0, yaw_range=0.2)),
     (15, dict(w_com=(1.0, 1.0, 200.0), w_pos=200.0, w_sym=0.0,
