@@ -563,6 +563,33 @@ CMPC_FN void recover_pass(Team T, const Config& cfg, const WorkS& w, double mu, 
             lamp.at(lane) = v;
             if (lane < NS) { w.lamn[N * ES + lane] = v; w.dlam[N * ES + lane] = v - w.lam[N * ES + lane]; }
         CMPC_WARP0_END
+#if defined(__CUDA_ARCH__)
+        // the operands of knot k - 1 (global memory) are fetched while knot k runs: the chain of a step is two shuffles and three
+        // multiply-adds instead of an L2 / DRAM round trip (the other warps of the team wait for this chain at the barrier)
+        if (T.lane < 32 && T.on) {
+            const int lane = T.lane;
+            const bool act = lane < NS;
+            int rr[2] = {0, 0};
+            if (act) acol_rows(lane, rr);
+            const double* vcop = w.vco + lane;
+            const double* awp = w.aw + 2 * lane;
+            const double* lamq = w.lam + lane;
+            double vn = act ? vcop[(N - 1) * ES] : 0.0, a0n = act ? awp[(N - 1) * AWS] : 0.0, a1n = act ? awp[(N - 1) * AWS + 1] : 0.0;
+            double ln = act ? lamq[(N - 1) * ES] : 0.0;
+            CMPC_ROLLED
+            for (int k = N - 1; k >= 0; --k) {
+                const double g0 = __shfl_sync(0xffffffffu, lamp.r, rr[0]), g1 = __shfl_sync(0xffffffffu, lamp.r, rr[1]);
+                const double vc = vn, a0 = a0n, a1 = a1n, lc = ln;
+                if (k > 0 && act) { vn = vcop[(k - 1) * ES]; a0n = awp[(k - 1) * AWS]; a1n = awp[(k - 1) * AWS + 1]; ln = lamq[(k - 1) * ES]; }
+                if (act) {
+                    const double v = fma(a1, g1, fma(a0, g0, lamp.r - vc));
+                    lamp.r = v;
+                    w.lamn[k * ES + lane] = v;
+                    w.dlam[k * ES + lane] = v - lc;
+                }
+            }
+        }
+#else
         CMPC_IF_WARP0
         {
             CMPC_ROLLED
@@ -581,6 +608,7 @@ CMPC_FN void recover_pass(Team T, const Config& cfg, const WorkS& w, double mu, 
                 CMPC_WARP0_END
             }
         }
+#endif
     }
     team_sync<NT, G>(T);
 }

@@ -24,6 +24,9 @@
 
 namespace cmpc {
 
+#ifndef CMPC_REDUCE_INTERLEAVED
+#define CMPC_REDUCE_INTERLEAVED 1
+#endif
 // ------------------------------------------------------------------------------------------------ device CTA context
 struct DevCta {
     int tid, nt, warp, lane, wsize;
@@ -65,6 +68,24 @@ struct DevCta {
     {
         constexpr int K = KM + KN + KS;
         const int nw = nt >> 5;
+#if CMPC_REDUCE_INTERLEAVED
+        // the K butterflies side by side: 5 rounds of K independent shuffles instead of K chains of 5 dependent ones
+        double x[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) x[k] = k < KM ? vmax[k] : (k < KM + KN ? vmin[k - KM] : vsum[k - KM - KN]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            double y[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) y[k] = __shfl_xor_sync(0xffffffffu, x[k], off);
+#pragma unroll
+            for (int k = 0; k < K; ++k) x[k] = k < KM ? fmax(x[k], y[k]) : (k < KM + KN ? fmin(x[k], y[k]) : x[k] + y[k]);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) red[warp * K + k] = x[k];
+        }
+#else
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int op = k < KM ? 0 : (k < KM + KN ? 1 : 2);
@@ -72,13 +93,36 @@ struct DevCta {
             const double x = warp_reduce_op(*src, op);
             if (lane == 0) red[warp * K + k] = x;
         }
+#endif
         bsync();
+#if CMPC_REDUCE_INTERLEAVED
+        {   // the K statistics of all warps: independent loads first, then K short combines
+            double z[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) z[k] = red[k];
+#pragma unroll 1
+            for (int w2 = 1; w2 < nw; ++w2) {
+                double y[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) y[k] = red[w2 * K + k];
+#pragma unroll
+                for (int k = 0; k < K; ++k) z[k] = k < KM ? fmax(z[k], y[k]) : (k < KM + KN ? fmin(z[k], y[k]) : z[k] + y[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (k < KM) vmax[k] = z[k];
+                else if (k < KM + KN) vmin[k - KM] = z[k];
+                else vsum[k - KM - KN] = z[k];
+            }
+        }
+#else
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int op = k < KM ? 0 : (k < KM + KN ? 1 : 2);
             double* dst = k < KM ? vmax + k : (k < KM + KN ? vmin + (k - KM) : vsum + (k - KM - KN));
             *dst = combine_warps(red + k, K, nw, op);
         }
+#endif
         bsync();
     }
     // statistic k of all warps (one copy of the code: the passes are bound by their instruction footprint)
