@@ -35,6 +35,9 @@ namespace cmpc {
 // invariant in the inner loop over the knots and hoisted out of it, the knot index is uniform over the warp, and the loads of
 // consecutive knots are independent of each other (the passes are bound by their instruction count: profiles/r1_notes.md)
 #define CMPC_ROLES(nroles) for (int r = lane & 31; r < (nroles); r += 32)
+#ifndef CMPC_HOIST_LOADS
+#define CMPC_HOIST_LOADS 1
+#endif
 #ifndef CMPC_KNOTS_UNROLL
 #define CMPC_KNOTS_UNROLL 1
 #endif
@@ -310,14 +313,13 @@ CMPC_FN void eval_point(Team T, Cta& cta, const Config& cfg, ISmem& sm, const do
                 else if (r >= 9) { const double e = zk[r] - t[T_NOM + r - 9]; acc[0] += cfg.w_pos * e * e; }
             } else if (k < N && r >= 16 && r < 16 + 38) {
                 const int l = r - 16, pr = k * PS + l;
+                const double sl = w.lo[pr], su = w.up[pr], s = slsrc[pr];   // requested together with the operands of the row value
                 const double g = path_dot(t, zk, zsrc + (k + 1) * ZS, l, 1);
                 w.gp[pr] = g;
-                const double sl = w.lo[pr], su = w.up[pr];
                 const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
                 if (hl || hu) {
                     if (sl == su) acc[1] += fabs(g - sl);
                     else {
-                        const double s = slsrc[pr];
                         acc[1] += fabs(g - s);
                         if (hl) acc[2] -= log(s - sl);
                         if (hu) acc[2] -= log(su - s);
@@ -385,8 +387,9 @@ CMPC_FN void kkt_pass(Team T, Cta& cta, const Config& cfg, ISmem& sm)
             if (r < NS + NU) {
                 if (k == N && r >= NS) continue;
                 const double g = grad_entry(cfg, w, w.z, k, r);
+                const double jt = jty_entry(cfg, w, w.lam, w.yp, k, r);   // its loads before the store below (a store pins the loads behind it)
                 w.gr[k * ZS + r] = g;
-                vmax[0] = fmax(vmax[0], fabs(g + jty_entry(cfg, w, w.lam, w.yp, k, r)));
+                vmax[0] = fmax(vmax[0], fabs(g + jt));
                 if (r < NS) {  // the equality row that defines s_k[r]
                     const int e = k * ES + r;
                     vmax[1] = fmax(vmax[1], fabs(w.ceq[e]));
@@ -395,18 +398,17 @@ CMPC_FN void kkt_pass(Team T, Cta& cta, const Config& cfg, ISmem& sm)
                 }
             } else if (k < N && r >= 48) {
                 const int pr = k * PS + r - 48;
-                const double sl = w.lo[pr], su = w.up[pr];
+                // (all global operands of the row requested before the first branch: one round trip, see recover_pass)
+                const double sl = w.lo[pr], su = w.up[pr], y = w.yp[pr], g = w.gp[pr], s = w.sl[pr], zlv = w.zl[pr], zuv = w.zu[pr];
                 const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
                 if (!hl && !hu) continue;
-                const double y = w.yp[pr], g = w.gp[pr];
                 vsum[0] += fabs(y);
                 vsum[3] += 1.0;
                 if (sl == su) { vmax[1] = fmax(vmax[1], fabs(g - sl)); continue; }
-                const double s = w.sl[pr];
                 vmax[1] = fmax(vmax[1], fabs(g - s));
                 double dsl = -y;
-                if (hl) { const double z = w.zl[pr], pd = (s - sl) * z; dsl -= z; vsum[1] += z; vsum[2] += 1.0; vmax[2] = fmax(vmax[2], pd); vmin[0] = fmin(vmin[0], pd); }
-                if (hu) { const double z = w.zu[pr], pd = (su - s) * z; dsl += z; vsum[1] += z; vsum[2] += 1.0; vmax[2] = fmax(vmax[2], pd); vmin[0] = fmin(vmin[0], pd); }
+                if (hl) { const double z = zlv, pd = (s - sl) * z; dsl -= z; vsum[1] += z; vsum[2] += 1.0; vmax[2] = fmax(vmax[2], pd); vmin[0] = fmin(vmin[0], pd); }
+                if (hu) { const double z = zuv, pd = (su - s) * z; dsl += z; vsum[1] += z; vsum[2] += 1.0; vmax[2] = fmax(vmax[2], pd); vmin[0] = fmin(vmin[0], pd); }
                 vmax[0] = fmax(vmax[0], fabs(dsl));
             }
         }
@@ -514,6 +516,30 @@ CMPC_FN void recover_pass(Team T, const Config& cfg, const WorkS& w, double mu, 
             const int l = r;
             if (l < 38) {
                 const int pr = k * PS + l;
+#if defined(__CUDA_ARCH__) && CMPC_HOIST_LOADS
+                // every global operand of the row is requested before the first branch on any of them: one round trip per row
+                // instead of bounds -> (row value, slack) -> multipliers
+                const double sl = w.lo[pr], su = w.up[pr], gpv = w.gp[pr], sv = w.sl[pr], ypv = w.yp[pr], zlv = w.zl[pr], zuv = w.zu[pr],
+                             sgv = w.sig[pr], cclv = pc ? w.ccl[pr] : 0.0, ccuv = pc ? w.ccu[pr] : 0.0;
+                const double jd = path_dot(w.tab + k * TS, w.dz + k * ZS, w.dz + (k + 1) * ZS, l, 0);
+                const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
+                double ds = 0.0, dzl = 0.0, dzu = 0.0, dy = 0.0;
+                if (hl || hu) {
+                    if (sl == su) dy = (jd + (gpv - sl)) / dc;
+                    else {
+                        ds = jd + (gpv - sv);
+                        double rs = -ypv;
+                        const double ml = mu - cclv, mup = mu + ccuv;
+                        if (hl) { const double rd = 1.0 / (sv - sl); rs -= ml * rd; dzl = ml * rd - zlv - zlv * rd * ds; }
+                        if (hu) { const double rd = 1.0 / (su - sv); rs += mup * rd; dzu = mup * rd - zuv + zuv * rd * ds; }
+                        if (hl && !hu) rs += KAPPA_D * mu;
+                        if (hu && !hl) rs -= KAPPA_D * mu;
+                        dy = sgv * ds + rs;
+                    }
+                }
+                w.dsl[pr] = ds; w.dzl[pr] = dzl; w.dzu[pr] = dzu; w.dyp[pr] = dy;
+                w.ypn[pr] = ypv + dy;
+#else
                 const double sl = w.lo[pr], su = w.up[pr];
                 const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
                 double ds = 0.0, dzl = 0.0, dzu = 0.0, dy = 0.0;
@@ -535,6 +561,7 @@ CMPC_FN void recover_pass(Team T, const Config& cfg, const WorkS& w, double mu, 
                 }
                 w.dsl[pr] = ds; w.dzl[pr] = dzl; w.dzu[pr] = dzu; w.dyp[pr] = dy;
                 w.ypn[pr] = w.yp[pr] + dy;
+#endif
             } else if (l >= 40 && l < 46) {  // step of the total force of contact c (for the bilinear hessian terms)
                 const int q = l - 40, c = q / 3, a = q - 3 * c;
                 const double* dc4 = w.dz + k * ZS + NS + 6 + 12 * c + a;
@@ -629,14 +656,14 @@ CMPC_FN void affine_pass(Team T, Cta& cta, const Config& cfg, ISmem& sm, double 
     CMPC_LANES
         CMPC_ROLES(38) CMPC_KNOTS(0, N - 1) {
             const int pr = k * PS + r;
-            const double sl = w.lo[pr], su = w.up[pr];
+            const double sl = w.lo[pr], su = w.up[pr], s = w.sl[pr], gpv = w.gp[pr], zlv = w.zl[pr], zuv = w.zu[pr];
+            const double jd = path_dot(w.tab + k * TS, w.dz + k * ZS, w.dz + (k + 1) * ZS, r, 0);
             const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
             double cl = 0.0, cu = 0.0, rl = 0.0, ru = 0.0;
             if ((hl || hu) && !(sl == su)) {
-                const double s = w.sl[pr];
-                const double ds = path_dot(w.tab + k * TS, w.dz + k * ZS, w.dz + (k + 1) * ZS, r, 0) + (w.gp[pr] - s);
+                const double ds = jd + (gpv - s);
                 if (hl) {
-                    const double d = s - sl, z = w.zl[pr];
+                    const double d = s - sl, z = zlv;
                     rl = 1.0 / d;
                     const double q = ds * rl, dzv = -z - z * q;
                     vmax[0] = fmax(vmax[0], -q); vmax[1] = fmax(vmax[1], 1.0 + q);
@@ -644,7 +671,7 @@ CMPC_FN void affine_pass(Team T, Cta& cta, const Config& cfg, ISmem& sm, double 
                     cl = ds * dzv;
                 }
                 if (hu) {
-                    const double d = su - s, z = w.zu[pr];
+                    const double d = su - s, z = zuv;
                     ru = 1.0 / d;
                     const double q = ds * ru, dzv = -z + z * q;
                     vmax[0] = fmax(vmax[0], q); vmax[1] = fmax(vmax[1], 1.0 - q);
@@ -724,21 +751,21 @@ CMPC_FN void step_pass(Team T, Cta& cta, const Config& cfg, ISmem& sm, double mu
                 if (!(fabs(d) < HUGE_VAL)) vmax[1] = 1.0;
             } else if (k < N && r >= 48) {
                 const int pr = k * PS + r - 48;
-                const double sl = w.lo[pr], su = w.up[pr];
+                const double sl = w.lo[pr], su = w.up[pr], s = w.sl[pr], ds = w.dsl[pr], dzlv = w.dzl[pr], dzuv = w.dzu[pr],
+                             zlv = w.zl[pr], zuv = w.zu[pr];
                 const bool hl = sl > -HUGE_VAL, hu = su < HUGE_VAL;
                 if ((!hl && !hu) || sl == su) continue;
-                const double s = w.sl[pr], ds = w.dsl[pr];
                 if (hl) {
-                    const double dd = s - sl, dz = w.dzl[pr];
+                    const double dd = s - sl, dz = dzlv;
                     vsum[0] -= mu * ds / dd;
                     if (ds < 0) vmin[0] = fmin(vmin[0], -tau * dd / ds);
-                    if (dz < 0) vmin[1] = fmin(vmin[1], -tau * w.zl[pr] / dz);
+                    if (dz < 0) vmin[1] = fmin(vmin[1], -tau * zlv / dz);
                 }
                 if (hu) {
-                    const double dd = su - s, dz = w.dzu[pr];
+                    const double dd = su - s, dz = dzuv;
                     vsum[0] += mu * ds / dd;
                     if (ds > 0) vmin[0] = fmin(vmin[0], tau * dd / ds);
-                    if (dz < 0) vmin[1] = fmin(vmin[1], -tau * w.zu[pr] / dz);
+                    if (dz < 0) vmin[1] = fmin(vmin[1], -tau * zuv / dz);
                 }
                 if (hl && !hu) vsum[0] += KAPPA_D * mu * ds;
                 if (hu && !hl) vsum[0] -= KAPPA_D * mu * ds;
