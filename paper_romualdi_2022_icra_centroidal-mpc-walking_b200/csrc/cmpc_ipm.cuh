@@ -370,13 +370,11 @@ CMPC_FN void kkt_pass(Team T, Cta& cta, const Config& cfg, ISmem& sm)
     const int N = cfg.N;
     // the values of the off-diagonal non-zeros of A at the iterate (needed by jty_entry and by the adjoint recursion)
     CMPC_LANES
-        CMPC_ROLES(NS) CMPC_KNOTS(0, N - 1) {
-            const int i = r;
-            {
-                double v2[2];
-                acol_vals(i, w.sd + k * SD_STRIDE, cfg.dT, v2);
-                w.aw[k * AWS + 2 * i] = v2[0]; w.aw[k * AWS + 2 * i + 1] = v2[1];
-            }
+        for (int it = lane; it < N * NS; it += NT) {   // 15 roles would leave half of every warp idle on each of its knots: flat
+            const int k = it / NS, i = it - NS * k;
+            double v2[2];
+            acol_vals(i, w.sd + k * SD_STRIDE, cfg.dT, v2);
+            w.aw[k * AWS + 2 * i] = v2[0]; w.aw[k * AWS + 2 * i + 1] = v2[1];
         }
     CMPC_LANES_END
     double vmax[3] = {0.0, 0.0, -HUGE_VAL};   // dual, viol, pmax
@@ -511,10 +509,8 @@ CMPC_FN void recover_pass(Team T, const Config& cfg, const WorkS& w, double mu, 
 {
     cta_align<G>(T);
     const int N = cfg.N;
-    CMPC_LANES
-        CMPC_ROLES(46) CMPC_KNOTS(0, N - 1) {
-            const int l = r;
-            if (l < 38) {
+    auto row = [&](int k, int l) {   // friction rows role major, step-box rows and the force sums flat: see affine_pass
+            {
                 const int pr = k * PS + l;
 #if defined(__CUDA_ARCH__) && CMPC_HOIST_LOADS
                 // every global operand of the row is requested before the first branch on any of them: one round trip per row
@@ -562,16 +558,20 @@ CMPC_FN void recover_pass(Team T, const Config& cfg, const WorkS& w, double mu, 
                 w.dsl[pr] = ds; w.dzl[pr] = dzl; w.dzu[pr] = dzu; w.dyp[pr] = dy;
                 w.ypn[pr] = w.yp[pr] + dy;
 #endif
-            } else if (l >= 40 && l < 46) {  // step of the total force of contact c (for the bilinear hessian terms)
-                const int q = l - 40, c = q / 3, a = q - 3 * c;
-                const double* dc4 = w.dz + k * ZS + NS + 6 + 12 * c + a;
-                w.dfc[k * 8 + q] = dc4[0] + dc4[3] + dc4[6] + dc4[9];
             }
+    };
+    CMPC_LANES
+        CMPC_ROLES(32) CMPC_KNOTS(0, N - 1) row(k, r);
+        for (int it = lane; it < N * 6; it += NT) { const int k = it / 6; row(k, 32 + it - 6 * k); }
+        for (int it = lane; it < N * 6; it += NT) {   // step of the total force of contact c (for the bilinear hessian terms)
+            const int k = it / 6, q = it - 6 * k, c = q / 3, a = q - 3 * c;
+            const double* dc4 = w.dz + k * ZS + NS + 6 + 12 * c + a;
+            w.dfc[k * 8 + q] = dc4[0] + dc4[3] + dc4[6] + dc4[9];
         }
     CMPC_LANES_END
     CMPC_LANES
-        CMPC_ROLES(NS) CMPC_KNOTS(0, N) {
-            const int i = r;
+        for (int it = lane; it < (N + 1) * NS; it += NT) {   // flat (15 roles: see kkt_pass)
+            const int k = it / NS, i = it - NS * k;
             double v = w.gr[k * ZS + i] + hess_dz_entry(cfg, w, dw, k, i);
             if (k > 0 && i >= 9) {
                 const int c = (i - 9) / 3, a = (i - 9) % 3;
@@ -653,8 +653,10 @@ CMPC_FN void affine_pass(Team T, Cta& cta, const Config& cfg, ISmem& sm, double 
     const int N = cfg.N;
     double vmax[2] = {1.0, 1.0};                  // 1 / alpha_aff (primal), 1 / alpha_aff (dual)
     double vsum[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // s00, s10, s01, s11, number of bounds
-    CMPC_LANES
-        CMPC_ROLES(38) CMPC_KNOTS(0, N - 1) {
+    // The 32 friction rows of a knot fill a warp (role major: lane = row, warps split the knots); the 6 step-box rows would
+    // leave 26 lanes idle on a second trip through the knots: they are taken flat (item = knot x row) in one trip of the team.
+    // A trip costs a memory round trip plus its instructions whatever the number of active lanes.
+    auto row = [&](int k, int r) {
             const int pr = k * PS + r;
             const double sl = w.lo[pr], su = w.up[pr], s = w.sl[pr], gpv = w.gp[pr], zlv = w.zl[pr], zuv = w.zu[pr];
             const double jd = path_dot(w.tab + k * TS, w.dz + k * ZS, w.dz + (k + 1) * ZS, r, 0);
@@ -681,7 +683,10 @@ CMPC_FN void affine_pass(Team T, Cta& cta, const Config& cfg, ISmem& sm, double 
             }
             w.ccl[pr] = cl; w.ccu[pr] = cu;
             w.dzl[pr] = rl; w.dzu[pr] = ru;   // scratch until the recover pass: 1 / distance to the bound
-        }
+    };
+    CMPC_LANES
+        CMPC_ROLES(32) CMPC_KNOTS(0, N - 1) row(k, r);
+        for (int it = lane; it < N * 6; it += NT) { const int k = it / 6; row(k, 32 + it - 6 * k); }
     CMPC_LANES_END_NOSYNC
     cta.template reduce3<2, 0, 5>(vmax, vmax, vsum);
     if (T.on && vsum[4] > 0.0 && vsum[0] > 0.0) {
@@ -693,10 +698,9 @@ CMPC_FN void affine_pass(Team T, Cta& cta, const Config& cfg, ISmem& sm, double 
     }
     const double mun = mu;
     CMPC_LANES
-        CMPC_ROLES(38) CMPC_KNOTS(0, N - 1) {
-            const int pr = k * PS + r;
-            const double rl = w.dzl[pr], ru = w.dzu[pr];
-            double dt = ru * (mun + w.ccu[pr]) - rl * (mun - w.ccl[pr]);
+        for (int pr = lane; pr < N * PS; pr += NT) {   // flat: nothing here depends on the role (the two pad rows of a knot hold zeros)
+            const double rl = w.dzl[pr], ru = w.dzu[pr], cu = w.ccu[pr], cl = w.ccl[pr];
+            double dt = ru * (mun + cu) - rl * (mun - cl);
             if (rl != 0.0 && ru == 0.0) dt += KAPPA_D * mun;
             if (ru != 0.0 && rl == 0.0) dt -= KAPPA_D * mun;
             w.dyp[pr] = dt;
