@@ -707,26 +707,33 @@ CMPC_FN void affine_pass(Team T, Cta& cta, const Config& cfg, ISmem& sm, double 
         }
     CMPC_LANES_END
     CMPC_LANES
-        CMPC_ROLES(NS + NU) CMPC_KNOTS(0, N) {
+        // J_path' dt touches 30 of the 45 variables of a knot (24 corner forces, 6 foot positions): exactly one warp of roles;
+        // the other 15 entries are zeros, written flat (two trips of the team instead of a second, half-empty role trip per knot)
+        CMPC_ROLES(30) CMPC_KNOTS(0, N) {
             double v = 0.0;
-            if (r < NS) {
-                if (k > 0 && r >= 9) {
-                    const int c = (r - 9) / 3, a = (r - 9) % 3;
+            int e;   // entry of the knot's variable block
+            if (r >= 24) {
+                const int q = r - 24, c = q / 3, a = q - 3 * c;
+                e = 9 + q;
+                if (k > 0) {
                     const double* R = w.tab + (k - 1) * TS + T_R + 9 * c;
                     const double* tb = w.dyp + (k - 1) * PS + 32 + 3 * c;
                     v = R[a] * tb[0] + R[3 + a] * tb[1] + R[6 + a] * tb[2];
                 }
             } else {
                 if (k == N) continue;
-                const int u = r - NS;
-                if (u >= 6) {
-                    const int f = u - 6, c = f / 12, j = (f % 12) / 3, a = f % 3;
-                    const double* ar = w.tab + k * TS + T_AR + 12 * c + a;  // row q at ar[3 q]
-                    const double* tf = w.dyp + k * PS + 16 * c + 4 * j;
-                    v = ar[0] * tf[0] + ar[3] * tf[1] + ar[6] * tf[2] + ar[9] * tf[3];
-                }
+                const int f = r, c = f / 12, j = (f % 12) / 3, a = f % 3;
+                e = NS + 6 + f;
+                const double* ar = w.tab + k * TS + T_AR + 12 * c + a;  // row q at ar[3 q]
+                const double* tf = w.dyp + k * PS + 16 * c + 4 * j;
+                v = ar[0] * tf[0] + ar[3] * tf[1] + ar[6] * tf[2] + ar[9] * tf[3];
             }
-            w.res[k * ZS + r] = v;
+            w.res[k * ZS + e] = v;
+        }
+        for (int it = lane; it < (N + 1) * 15; it += NT) {   // s rows 0 .. 8 and the contact velocities
+            const int k = it / 15, q = it - 15 * k;
+            if (k == N && q >= 9) continue;
+            w.res[k * ZS + (q < 9 ? q : NS + q - 9)] = 0.0;
         }
     CMPC_LANES_END
 }
