@@ -44,14 +44,14 @@ PKG = "paper_romualdi_2022_icra_centroidal-mpc-walking_b200"
 # smsp__sass_thread_inst_executed_op_{dfma x 2, dadd, dmul}_pred_on of one launch / (iterations x knots), see profiles/ and
 # DESIGN.md "flop accounting"; the per-iteration-and-knot work does not depend on the workload: the same code runs for every
 # robot, horizon and batch), and the canonical dense figure of SURVEY.md 8(d)
-# Round 2: the stage factorisation and the SYRK run on the FP64 tensor cores: 1.861e5 = (2 x 5.922e9 DFMA + 2.026e9 DADD +
-# 2.410e9 DMUL thread instructions + 1.7287e10 tensor-core flop [sm__ops_path_tensor_src_fp64.sum]) / (12024 iterations x 15
-# knots) of capture r2_prof_final (profiles/r2_notes.md); 9.6e4 of it are DMMA flop on padded 8 x 8 tiles (round 1 executed
+# Round 2: the stage factorisation and the SYRK run on the FP64 tensor cores: 1.839e5 = (2 x 5.814e9 DFMA + 1.861e9 DADD +
+# 2.395e9 DMUL thread instructions + 1.7285e10 tensor-core flop [sm__ops_path_tensor_src_fp64.sum]) / (12024 iterations x 15
+# knots) of capture r2_prof_final3 (profiles/r2_notes.md); 9.6e4 of it are DMMA flop on padded 8 x 8 tiles (round 1 executed
 # 1.19e5 on 3 x 3 tiles that skipped structural zeros).  monotone: round 1's figure + the same DMMA surplus (not re-captured).
-FLOP_EXEC_PER_ITER_KNOT = {"monotone": 1.89e5, "mehrotra": 1.861e5}
+FLOP_EXEC_PER_ITER_KNOT = {"monotone": 1.87e5, "mehrotra": 1.839e5}
 FLOP_CANON_PER_ITER_KNOT = 422275.0
 # measured DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum), keyed by (workload, batch, strategy)
-DRAM_TRAFFIC_PER_LAUNCH = {("icub3_b1024", 1024, "mehrotra"): 1.211e10}   # r2_prof_final: 7.88 GB read + 4.23 GB written
+DRAM_TRAFFIC_PER_LAUNCH = {("icub3_b1024", 1024, "mehrotra"): 1.228e10}   # r2_prof_final3: 8.02 GB read + 4.26 GB written
 # ipopt_tolerance of the robot ini each workload is built from (config/robots/<robot>/centroidal_mpc.ini)
 INI_TOLERANCE = {"icub3_b1024": 1e-8, "ergocub_b65536": 1e-4}
 FP64_PEAK_FALLBACK_TFLOPS = 37.0  # vendor figure (HGX B200 296 TF / 8); used only if the live DFMA probe fails

@@ -21,7 +21,7 @@ import torch  # noqa: E402
 
 from oracle import oracle as om  # noqa: E402  (reported CPU baseline, never the thing measured on the GPU side)
 
-FLOP_PER_ITER_KNOT = 1.861e5   # executed FP64 flop per iteration and knot (ncu capture r2_prof_final, see bench.py)
+FLOP_PER_ITER_KNOT = 1.839e5   # executed FP64 flop per iteration and knot (ncu capture r2_prof_final3, see bench.py)
 om.build()
 O = om.Oracle()
 CORES = os.cpu_count() or 1
