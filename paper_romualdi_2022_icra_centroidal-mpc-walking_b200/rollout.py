@@ -140,9 +140,16 @@ def closed_loop_rollout_device(solver: BatchedCentroidalMPC, B: int, ticks: int,
         tick(True)
         if ticks > 1:
             if use_graph:
+                # capture_begin / capture_end directly: the torch.cuda.graph() context manager synchronises, runs the garbage
+                # collector and empties the allocator's cache on entry -- 0.3 - 0.9 s of host time in a process that holds tens
+                # of GB of cached blocks, spent between the first tick and the first replay with the device idle
+                # (profiles/r2_notes.md section 10).  Nothing is allocated through torch inside the captured tick.
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, stream=stream):
+                graph.capture_begin()
+                try:
                     tick(False)
+                finally:
+                    graph.capture_end()
                 # capturing does not execute: the captured tick is launched T - 1 times
                 for _ in range(ticks - 1):
                     graph.replay()
